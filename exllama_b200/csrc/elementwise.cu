@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) rms_norm_kernel(const half* __restrict__ 
     const half* xr = x + (size_t)row * dim;
     half* orow = out + (size_t)row * dim;
     float ss = 0.f;
-    const int nv = dim / 8;
+    const int nv = (dim % 8 == 0) ? dim / 8 : 0;     // 16-byte vector path needs every row 16-byte aligned
     for (int i = tid; i < nv; i += 256) {
         uint4 v = reinterpret_cast<const uint4*>(xr)[i];
         const half2* h = reinterpret_cast<const half2*>(&v);
