@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libexl_b200.so")
+LIB_PATH = os.environ.get("EXL_B200_LIB", os.path.join(_HERE, "libexl_b200.so"))   # env override: dev experiments only
 _lib = None
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float

@@ -1,0 +1,93 @@
+"""Tensor-parallel sharding of a GPTQ Llama layer and the per-projection all-reduce.
+
+The reference has no tensor parallelism (only a sequential layer split, model.py:636-668); this is new
+functionality on top of the operator surface:
+
+  column-parallel (no exchange):  q, k, v  -> whole heads per rank;   gate, up -> column blocks per rank
+  row-parallel (one all-reduce):  o_proj (rows = local heads' channels),  down_proj (rows = local gate/up columns)
+
+Row shards must start on quantisation-group boundaries so qzeros/scales slice cleanly; when the number of groups
+does not divide by the TP degree (65B: 22016 / 128 = 172 groups over 8 ranks) ranks get floor/ceil whole groups.
+
+`plan_shards` and `shard_q4_*` are pure index arithmetic (tested on the CPU with numpy + gloo);
+`row_parallel_residual` / `mlp_tp` issue the GPU ops through the plugin API and NCCL.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class ShardPlan:
+    tp: int
+    heads: list            # heads per rank
+    head_cols: list        # (col0, col1) of q/k/v columns == o_proj rows per rank
+    inter_cols: list       # (col0, col1) of gate/up columns == down_proj rows per rank
+
+
+def _split_even(total_units, tp):
+    base, rem = divmod(total_units, tp)
+    sizes = [base + (1 if r < rem else 0) for r in range(tp)]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    return sizes, offs
+
+
+def plan_shards(hidden, inter, heads, head_dim, groupsize, tp) -> ShardPlan:
+    if heads % tp != 0:
+        raise ValueError(f"{heads} heads do not divide over {tp} ranks (whole heads per rank are required)")
+    hp = heads // tp
+    if (hp * head_dim) % groupsize != 0 and tp > 1:
+        raise ValueError("o_proj row shard is not aligned to the quantisation group size")
+    head_cols = [(r * hp * head_dim, (r + 1) * hp * head_dim) for r in range(tp)]
+    # intermediate dim: whole groups per rank, also a multiple of 128 columns for the kernels' tiles
+    unit = int(np.lcm(groupsize, 128))
+    if inter % unit != 0:
+        unit = groupsize
+    sizes, offs = _split_even(inter // unit, tp)
+    inter_cols = [(offs[r] * unit, offs[r + 1] * unit) for r in range(tp)]
+    return ShardPlan(tp, [hp] * tp, head_cols, inter_cols)
+
+
+def shard_q4_columns(qweight, qzeros, scales, c0, c1):
+    """Column (N) shard of a GPTQ tensor set: works on numpy arrays or torch tensors."""
+    assert c0 % 8 == 0 and c1 % 8 == 0
+    return qweight[:, c0:c1], qzeros[:, c0 // 8:c1 // 8], scales[:, c0:c1]
+
+
+def shard_q4_rows(qweight, qzeros, scales, k0, k1, groupsize):
+    """Row (K) shard on group boundaries (no act-order)."""
+    assert k0 % groupsize == 0 and k1 % groupsize == 0 and k0 % 8 == 0
+    return qweight[k0 // 8:k1 // 8], qzeros[k0 // groupsize:k1 // groupsize], scales[k0 // groupsize:k1 // groupsize]
+
+
+def all_reduce(t, group=None):
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def row_parallel_residual(ext, x, inp, q4, rank, group):
+    """x (replicated, [M, hidden]) += all_reduce(inp_local . W_rowshard).
+    Rank 0 folds the residual into its partial (no_zero accumulate, exactly q4_attn_2); the other ranks
+    overwrite their copy of x with their partial, so one in-place all-reduce leaves x_old + sum(partials) everywhere."""
+    import torch
+    from . import cuda_ext
+    none = cuda_ext.none_tensor
+    if rank == 0:
+        ext.q4_attn_2(x, inp, q4, none, none, none)
+    else:
+        ext.q4_matmul(inp, q4, x)
+    all_reduce(x, group)
+
+
+def mlp_tp(ext, cuda_ext, x, L, eps, rank, group):
+    """Tensor-parallel MLP block: local [norm -> gate,up -> silu*mul] then row-parallel down + all-reduce."""
+    import torch
+    none = cuda_ext.none_tensor
+    xn = cuda_ext.ext_rms_norm(x, L.ln2, eps)
+    g = cuda_ext.ext_q4_matmul(xn, L.gate.q4, L.gate.width)
+    u = cuda_ext.ext_q4_matmul(xn, L.up.q4, L.up.width)
+    act = torch.nn.functional.silu(g) * u
+    row_parallel_residual(ext, x, act, L.down.q4, rank, group)

@@ -110,4 +110,21 @@ void ref_q4_mlp(void* x, const void* rms_w, float eps, void* gate, void* up, voi
 
 int ref_sync() { return (int)cudaDeviceSynchronize(); }
 
+// Back-to-back launches of the reference decode kernel over a pool of matrices, timed with CUDA events on the
+// legacy default stream (what the reference launches on).  Returns mean microseconds per q4_matmul call.
+float ref_bench_q4_pool(const void* x, int M, void** handles, int n, void* out, int reps, int mode)
+{
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < n; i++) ref_q4_matmul(x, M, handles[i], out, 0, mode);
+    cudaDeviceSynchronize();
+    cudaEventRecord(a, 0);
+    for (int r = 0; r < reps; r++)
+        for (int i = 0; i < n; i++) ref_q4_matmul(x, M, handles[i], out, 0, mode);
+    cudaEventRecord(b, 0);
+    cudaEventSynchronize(b);
+    float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms * 1000.0f / (float)(reps * n);
+}
+
 }
