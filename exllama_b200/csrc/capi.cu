@@ -170,6 +170,7 @@ int exl_make_q4(void* qweight, void* qzeros, void* scales, const int32_t* g_idx_
             return rc != EXL_OK ? rc : exl_set_err(EXL_ERR_CUDA, "make_q4: %s", cudaGetErrorString(e));
         }
     }
+    if (int rc = exl_encode_weight_tmap(m)) { if (m->x_map) cudaFree(m->x_map); delete m; return rc; }
     {
         std::lock_guard<std::mutex> lock(g_mutex);
         g_matrices.push_back(m);

@@ -1,5 +1,6 @@
 // exl_common.cuh -- shared declarations for libexl_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cublas_v2.h>
@@ -22,6 +23,8 @@ struct exl_q4_matrix
     uint32_t* qzeros;    // [groups, N/8]
     half* scales;        // [groups, N]
     uint32_t* x_map;     // [K] or nullptr (act-order: x column feeding sequential row k)
+    // TMA descriptor of qweight as a 2-D int32 tensor [K/8, N], box 16 rows x 32 columns, 128-byte swizzle (q4_gemv.cu)
+    alignas(64) CUtensorMap tmap_w;
 };
 
 struct ExlTuning
@@ -109,6 +112,7 @@ int exl_gemv_launch(ExlDevice* ds, const half* x, int M, const exl_q4_matrix* co
                     int num_mats, bool no_zero, int prologue, int epilogue, const GemvFused* fused, cudaStream_t stream);
 
 // q4_matrix.cu
+int exl_encode_weight_tmap(exl_q4_matrix* w);
 int exl_reconstruct_launch(const exl_q4_matrix* w, half* out, cudaStream_t stream);
 
 // q4_gemm_tc.cu : tcgen05 fused-dequant GEMM (prefill)

@@ -5,10 +5,12 @@
 // rope (rope.cu), update_cache_kernel (q4_attn.cu:19-72) and silu_mul (q4_mlp.cu:46-88) on the decode path.
 //
 // Design (HBM-bound; see DESIGN.md "decode kernel"):
-//  * packed qweight [K/8, N] is streamed exactly once with 128-bit loads (ld.global.nc.L1::no_allocate.v4):
-//    lane (g = lane/4, t = lane%4) of a warp loads the 4 columns 4g..4g+3 of k8-row t, so one warp
-//    request covers 4 rows x 128 B and a CTA step (8 warps) covers 128 columns x 64 k.  GV_U steps are kept
-//    in flight per thread in registers.
+//  * packed qweight [K/8, N] is streamed exactly once: a producer warp moves 16-row x 128-column stages
+//    (8 KB = four 2-D TMA boxes of 16 rows x 32 columns, cp.async.bulk.tensor, SWIZZLE_128B) into a GV_NST-deep
+//    shared-memory ring guarded by mbarrier full/empty pairs, so ~50 KB per CTA are in flight without holding
+//    registers.  Consumer lane (g = lane/4, t = lane%4) reads 4 adjacent columns of k8-row t with one LDS.128;
+//    the column chunk a lane owns is pi(g) = (g >> 1) | ((g & 1) << 2), which makes the swizzled pattern
+//    bank-conflict free.
 //  * group scales / zeros of the CTA's k-range are staged into shared memory with 1-D TMA bulk copies
 //    (cp.async.bulk + mbarrier); x is staged by the threads because it is permuted (and gathered through the
 //    act-order x_map, and RMS-normalised for the fused decoder ops) on the way in.
@@ -18,35 +20,40 @@
 //    operand: exact fp16 products, fp32 accumulation, cost independent of M for M <= 8.
 //    K is traversed in the permuted order (0,4,1,5,2,6,3,7) inside each 8-block so no nibble shuffling is needed.
 //  * group scales are applied once per group to an fp32 group accumulator.
-//  * work is a flat list of (128-column tile, 64-k step) items split evenly over a persistent grid
-//    (stream-K): every CTA streams the same number of bytes whatever N and K are.  Tiles that span several
-//    CTAs are finished by the last CTA to arrive (partials in an L2-resident workspace, fixed summation
-//    order => deterministic; no fp16 atomics unlike the reference, q4_matmul.cu:203-211).
-//  * programmatic dependent launch: weights do not depend on the previous kernel, so a CTA prefetches its first
-//    GV_U steps of weights and its scales/zeros BEFORE griddepcontrol.wait, and signals launch_dependents as soon
-//    as its main loop is done -- back-to-back GEMVs keep HBM busy across the launch boundary.
+//  * split-K without global memory: one thread-block CLUSTER owns one 128-column tile; its CS CTAs take contiguous
+//    K slices and the leader sums the CS partials out of its own shared memory, where the peers deposited them
+//    through DSMEM (st.shared::cluster) before a cluster barrier.  Fixed summation order => deterministic; no fp16
+//    atomics (the reference: q4_matmul.cu:203-211) and no L2 round trips on the critical path.
+//  * programmatic dependent launch: weights do not depend on the previous kernel, so the producer warp fills the
+//    whole TMA ring BEFORE the consumers' griddepcontrol.wait, and launch_dependents is signalled as soon as the
+//    last weight stage has been issued -- back-to-back GEMVs keep HBM busy across the launch boundary.
 #include "exl_common.cuh"
 #include <cstdlib>
 #include <cstring>
 
-#ifndef GV_U
-#define GV_U 4                      // register prefetch depth (steps)
-#endif
-#ifndef GV_MINB
-#define GV_MINB 2                   // min CTAs per SM for __launch_bounds__
+#ifndef GV_NST
+#define GV_NST 6                    // TMA ring depth (stages of 16 k8-rows x 128 columns)
 #endif
 
 namespace {
 
-constexpr int THREADS = 256;
-constexpr int WN = 4;              // warps across columns (4 x 32 = 128 columns)
-constexpr int WK = 2;              // warps across k
-constexpr int STEP_K = 64;         // k per CTA step
-constexpr int U = GV_U;
+constexpr int CONSUMERS = 256;             // 8 consumer warps: 4 across columns x 2 across k
+constexpr int THREADS = CONSUMERS + 32;    // + 1 producer warp
+constexpr int WN = 4, WK = 2;
+constexpr int STAGE_ROWS = 16;             // k8-rows per ring stage (= 128 k)
+constexpr int STAGE_K = STAGE_ROWS * 8;
+constexpr int BOX_COLS = 32;                 // TMA box: 32 columns (128 B, SWIZZLE_128B) x 16 k8-rows = 2 KB, one per column-warp
+constexpr int BOX_BYTES = STAGE_ROWS * BOX_COLS * 4;
+constexpr int STAGE_BYTES = WN * BOX_BYTES;  // 8 KB
+constexpr int NST = GV_NST;
 constexpr int RED_LD = GV_TILE_N + 4;
-constexpr int GMAXC = 64;          // max quantisation groups staged per chunk
+constexpr int GMAXC = 16;                  // max quantisation groups staged per chunk
 constexpr int SC_ROW = GV_TILE_N * 2;      // bytes of scales per group row in smem
-constexpr int ZQ_ROW = GV_TILE_N / 2;      // bytes of packed zeros per group row in smem
+constexpr int ZQ_ROW = GV_TILE_N / 2;      // bytes of packed zeros per group row in smem (raw, as TMA delivers them)
+constexpr int ZS_ROW = GV_TILE_N * 4;      // bytes of expanded zero constants per group row: half2(1024 + zp) per column
+constexpr int XS_BUDGET = 16 * 1024;       // bytes of staged x per chunk
+constexpr int SLOT_BUDGET = 16 * 1024;     // bytes of cluster-reduction slots (2 x CS x M x 512 B)
+constexpr int MAX_CS = 8;
 
 struct GemvMatDev
 {
@@ -54,35 +61,26 @@ struct GemvMatDev
     int N; int tile0;
 };
 
-struct GemvArgs
+struct alignas(64) GemvArgs
 {
+    CUtensorMap tmaps[3];              // qweight of each fused matrix ([K/8, N] uint32, box 16 x 32, 128B swizzle)
     const half* x; const uint32_t* x_map;
     int M, K, groups, gs_shift32;      // gs_shift32: log2(groupsize / 32) (30 when there is a single group)
-    int spt;                           // steps per tile = ceil(K / 64)
-    int total_tiles;
-    long long total_steps;
+    int spt;                           // ring stages per tile = ceil(K / 128)
+    int cs;                            // cluster size == K split factor
     int num_mats;
     GemvMatDev mats[3];
     int no_zero;
-    int chunk_steps;                   // staging chunk (steps)
+    int chunk_stages;                  // staging chunk (ring stages)
     int xs_stride;                     // bytes, == 64 (mod 128)
-    float* partials; unsigned* counters;
     // fused prologue / epilogue
     const half* norm_w; float eps; float r_dim;
     const half* sin; const half* cos;
     int head_dim, num_heads, num_kv_heads, past_len, max_seq_len;
     half* key_cache; half* value_cache;
-    float* pair_stage; unsigned* pair_counters;   // GV_EPI_SILU_MUL
     int debug;                         // EXL_GV_DEBUG bitmask (profiling experiments only)
 };
 
-// predicated streaming load: keeps the old register contents when pred is false
-__device__ __forceinline__ void ldg_stream_v4_pred(uint4& r, const void* p, bool pred)
-{
-    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %5, 0;\n\t"
-                 "@pp ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
-                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((int)pred));
-}
 __device__ __forceinline__ float ldcg_f32(const float* p)
 {
     float r;
@@ -116,6 +114,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 2-D TMA tile load global -> shared (SASS: UTMALDG); c0 = column (uint32 elements), c1 = k8-row
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, void* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -173,39 +177,46 @@ struct Accum
     int cur_grp;
 };
 
-__device__ __forceinline__ void group_switch(Accum& A, int grp, int g_lo, const unsigned char* sc_s, const unsigned char* zq_s,
-                                             int lane_col /* wn*32 + 4g */)
+__device__ __forceinline__ void group_switch(Accum& A, int grp, int g_lo, uint32_t sc_addr, uint32_t zs_addr, int lane_col)
 {
     if (A.cur_grp >= 0) {
         #pragma unroll
         for (int j = 0; j < 8; j++) { A.acc[j] = fmaf(A.cs[j >> 1], A.cg[j], A.acc[j]); A.cg[j] = 0.f; }
     }
     const int gl = grp - g_lo;
-    const uint2 sc = *reinterpret_cast<const uint2*>(sc_s + gl * SC_ROW + lane_col * 2);
-    const uint32_t zw = *reinterpret_cast<const uint32_t*>(zq_s + gl * ZQ_ROW + (lane_col >> 3) * 4);
+    uint2 sc; uint4 z;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sc.x), "=r"(sc.y) : "r"(sc_addr + gl * SC_ROW + lane_col * 2));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(z.x), "=r"(z.y), "=r"(z.z), "=r"(z.w) : "r"(zs_addr + gl * ZS_ROW + lane_col * 4));
     const half2 s01 = *reinterpret_cast<const half2*>(&sc.x);
     const half2 s23 = *reinterpret_cast<const half2*>(&sc.y);
     A.cs[0] = __low2float(s01); A.cs[1] = __high2float(s01);
     A.cs[2] = __low2float(s23); A.cs[3] = __high2float(s23);
-    const uint32_t z4 = zw >> ((lane_col & 4) * 4);
+    // zs = half2(1024 + zp) comes from the staged table; zf = half2(-(64 + zp)) = 0xd400 + 16 * zp per half
+    A.zs[0] = z.x; A.zs[1] = z.y; A.zs[2] = z.z; A.zs[3] = z.w;
     #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t zp = ((z4 >> (4 * j)) & 0xfu) + 1u;
-        A.zs[j] = (0x6400u + zp) * 0x00010001u;            // half2(1024 + zp)
-        A.zf[j] = (0xd400u + (zp << 4)) * 0x00010001u;     // half2(-(64 + zp))
-    }
+    for (int j = 0; j < 4; j++) A.zf[j] = ((A.zs[j] & 0x001f001fu) << 4) | 0xd400d400u;
     A.cur_grp = grp;
 }
 
-__device__ __forceinline__ void unit_mma(Accum& A, const uint4& w, const uint4& xb)
+__device__ __forceinline__ void unit_mma(Accum& A, const uint4& w, const uint4& xb, int dbg = 0)
 {
     uint32_t p0[4], p1[4], p2[4], p3[4];
-    dequant_word(w.x, A.zs[0], A.zf[0], p0[0], p0[1], p0[2], p0[3]);
-    dequant_word(w.y, A.zs[1], A.zf[1], p1[0], p1[1], p1[2], p1[3]);
-    dequant_word(w.z, A.zs[2], A.zf[2], p2[0], p2[1], p2[2], p2[3]);
-    dequant_word(w.w, A.zs[3], A.zf[3], p3[0], p3[1], p3[2], p3[3]);
+    if (dbg & 16) {            // experiment: no unpack
+        p0[0] = w.x; p0[1] = w.y; p0[2] = w.z; p0[3] = w.w; p1[0] = w.y; p1[1] = w.z; p1[2] = w.w; p1[3] = w.x;
+        p2[0] = w.z; p2[1] = w.w; p2[2] = w.x; p2[3] = w.y; p3[0] = w.w; p3[1] = w.x; p3[2] = w.y; p3[3] = w.z;
+    } else {
+        dequant_word(w.x, A.zs[0], A.zf[0], p0[0], p0[1], p0[2], p0[3]);
+        dequant_word(w.y, A.zs[1], A.zf[1], p1[0], p1[1], p1[2], p1[3]);
+        dequant_word(w.z, A.zs[2], A.zf[2], p2[0], p2[1], p2[2], p2[3]);
+        dequant_word(w.w, A.zs[3], A.zf[3], p3[0], p3[1], p3[2], p3[3]);
+    }
     float (&cA)[4] = *reinterpret_cast<float (*)[4]>(&A.cg[0]);
     float (&cB)[4] = *reinterpret_cast<float (*)[4]>(&A.cg[4]);
+    if (dbg & 8) {             // experiment: no tensor-core work (keep the unpack alive)
+        cA[0] += __uint_as_float(p0[0] ^ p1[1] ^ p0[2] ^ p1[3] ^ xb.x); cA[1] += __uint_as_float(p1[0] ^ p0[1] ^ p1[2] ^ p0[3] ^ xb.y);
+        cB[0] += __uint_as_float(p2[0] ^ p3[1] ^ p2[2] ^ p3[3] ^ xb.z); cB[1] += __uint_as_float(p3[0] ^ p2[1] ^ p3[2] ^ p2[3] ^ xb.w);
+        return;
+    }
     // columns (c0, c1): rows g / g+8 of A;  k order (0,4,1,5) then (2,6,3,7)
     mma16816(cA, p0[0], p1[0], p0[1], p1[1], xb.x, xb.y);
     mma16816(cA, p0[2], p1[2], p0[3], p1[3], xb.z, xb.w);
@@ -213,55 +224,138 @@ __device__ __forceinline__ void unit_mma(Accum& A, const uint4& w, const uint4& 
     mma16816(cB, p2[2], p3[2], p2[3], p3[3], xb.z, xb.w);
 }
 
+__device__ __forceinline__ void mbar_arrive(void* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
+{
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" :: "r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int PRO, int EPI>
-__global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const GemvArgs a)
+__global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_constant__ GemvArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [sc_s: GMAXC * 256][zq_s: GMAXC * 64][red: WK * 8 * RED_LD * 4][xs: M * xs_stride]
-    unsigned char* sc_s = smem;
-    unsigned char* zq_s = smem + GMAXC * SC_ROW;
-    float* red = reinterpret_cast<float*>(smem + GMAXC * (SC_ROW + ZQ_ROW));
-    unsigned char* xs = smem + GMAXC * (SC_ROW + ZQ_ROW) + WK * GV_MAXM * RED_LD * sizeof(float);
-    __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ unsigned s_old;
+    const int cs = a.cs, M = a.M, K = a.K, spt = a.spt;
+    unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);    // NST x STAGE_BYTES, 1 KB aligned (swizzle atom)
+    unsigned char* sc_s = ring + NST * STAGE_BYTES;                               // GMAXC x 256
+    unsigned char* zq_s = sc_s + GMAXC * SC_ROW;                                  // GMAXC x 64 (raw packed zeros)
+    unsigned char* zs_s = zq_s + GMAXC * ZQ_ROW;                                  // GMAXC x 512 (half2(1024 + zp) per column)
+    float* red = reinterpret_cast<float*>(zs_s + GMAXC * ZS_ROW);                 // WK x 8 x RED_LD
+    float* slots = red + WK * GV_MAXM * RED_LD;                                   // 2 x cs x M x 128 (cluster reduction)
+    unsigned char* xs = reinterpret_cast<unsigned char*>(slots + 2 * cs * M * GV_TILE_N);   // M x xs_stride
+    __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST], sc_bar;
     __shared__ float s_rm[GV_MAXM];
-    __shared__ float s_wsum[THREADS / 32];
+    __shared__ float s_wsum[CONSUMERS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wn = warp & (WN - 1), wk = warp >> 2;
-    const int g = lane >> 2, t = lane & 3;
-    const int lane_col = wn * 32 + 4 * g;
-    const int M = a.M, K = a.K, spt = a.spt;
+    const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const int item = blockIdx.x / cs;
+    constexpr int NSUB = (EPI == GV_EPI_SILU_MUL) ? 2 : 1;
     const int k8_lim = K >> 3;
-    const long long G = gridDim.x;
-    const long long S0 = (long long)blockIdx.x * a.total_steps / G;
-    const long long S1 = (long long)(blockIdx.x + 1) * a.total_steps / G;
+    const int sg0 = rank * spt / cs, sg1 = (rank + 1) * spt / cs;       // this CTA's K slice, in ring stages
 
-    if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid == 0) {
+        #pragma unroll
+        for (int i = 0; i < NST; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], WN); }
+        mbar_init(&sc_bar, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    uint32_t bar_parity = 0;
-    bool waited_dep = false;       // griddepcontrol.wait executed (x / out / workspace may be touched after it)
+    if (cs > 1) cluster_arrive();          // #0: "this CTA is running" -- waited on before the first DSMEM store
 
-    long long s = S0;
-    while (s < S1) {
-        const int tile = (int)(s / spt);
-        const int st0 = (int)(s - (long long)tile * spt);
-        const int st1 = (int)min((long long)spt, (long long)st0 + (S1 - s));
-        int mi = 0;
-        if (EPI == GV_EPI_SILU_MUL) {
-            mi = tile & 1;                       // tiles alternate gate_j, up_j
-        } else {
-            if (a.num_mats > 1 && tile >= a.mats[1].tile0) mi = 1;
-            if (a.num_mats > 2 && tile >= a.mats[2].tile0) mi = 2;
+    // resolve (item, sub) -> matrix + column tile
+    auto resolve = [&](int sub, int& mi, int& ctile) {
+        if (EPI == GV_EPI_SILU_MUL) { mi = sub; ctile = item; }
+        else {
+            mi = 0;
+            if (a.num_mats > 1 && item >= a.mats[1].tile0) mi = 1;
+            if (a.num_mats > 2 && item >= a.mats[2].tile0) mi = 2;
+            ctile = item - (mi == 0 ? a.mats[0].tile0 : (mi == 1 ? a.mats[1].tile0 : a.mats[2].tile0));
         }
-        const uint32_t* qw = mi == 0 ? a.mats[0].qw : (mi == 1 ? a.mats[1].qw : a.mats[2].qw);
+    };
+
+    if (warp == CONSUMERS / 32) {
+        // =============================== producer warp: weight stages via TMA bulk copies ===============================
+        int j = 0, pslot = 0; uint32_t pphase = 0;     // pphase: parity of the fill the consumers are waiting for
+        for (int sub = 0; sub < NSUB; sub++) {
+            int mi, ctile; resolve(sub, mi, ctile);
+            const CUtensorMap* tm = &a.tmaps[mi];
+            const int N = mi == 0 ? a.mats[0].N : (mi == 1 ? a.mats[1].N : a.mats[2].N);
+            const int col_tile0 = ctile * GV_TILE_N;
+            const int nbox = (min(GV_TILE_N, N - col_tile0) + BOX_COLS - 1) / BOX_COLS;     // column-warps with real columns
+            for (int sg = sg0; sg < sg1; sg++, j++) {
+                const int slot = pslot;
+                if (j >= NST) mbar_wait(&empty_bar[slot], pphase ^ 1u);
+                const bool skip = (a.debug & 1) != 0;
+                // out-of-range rows / columns of a box are zero-filled by the TMA unit and still count as bytes
+                if (lane == 0) mbar_expect_tx(&full_bar[slot], skip ? 0u : (uint32_t)nbox * BOX_BYTES);
+                __syncwarp();
+                if (lane < nbox && !skip)
+                    tma_load_2d(ring + slot * STAGE_BYTES + lane * BOX_BYTES, tm, col_tile0 + lane * BOX_COLS, sg * STAGE_ROWS, &full_bar[slot]);
+                if (++pslot == NST) { pslot = 0; pphase ^= 1u; }
+            }
+            if (sub == NSUB - 1) pdl_launch_dependents();     // every weight byte of this CTA has been requested
+            if (cs > 1) { cluster_wait(); cluster_arrive(); }
+        }
+        if (cs > 1) cluster_wait();
+        return;
+    }
+
+    // =============================================== consumer warps ===============================================
+    const int wn = warp & (WN - 1), wk = warp >> 2;
+    const int g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) | ((g & 1) << 2);      // column chunk owned by this lane (bank-conflict-free with the 128B swizzle)
+    const int lane_col = wn * 32 + 4 * pg;
+    const int xrow = min(g, M - 1);
+    const int ecol = tid & (GV_TILE_N - 1);
+    const int em0 = tid >> 7;                 // 0 or 1; this thread owns rows em0, em0+2, em0+4, em0+6
+    uint32_t sc_parity = 0;
+    bool waited_dep = false;
+    int jbase = 0;                 // ring position of this sub-tile's first stage
+    float v[4] = {0.f, 0.f, 0.f, 0.f}, vprev[4] = {0.f, 0.f, 0.f, 0.f};
+    int mi = 0, ctile = 0;
+
+    auto sum_slots = [&](int buf, float (&o)[4]) {
+        #pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = 0.f;
+        for (int r = 0; r < cs; r++) {
+            const float* sp = slots + ((size_t)(buf * cs + r) * M) * GV_TILE_N;
+            #pragma unroll
+            for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) o[i] += sp[m * GV_TILE_N + ecol]; }
+        }
+    };
+
+    for (int sub = 0; sub < NSUB; sub++) {
+        resolve(sub, mi, ctile);
         const uint32_t* qz = mi == 0 ? a.mats[0].qz : (mi == 1 ? a.mats[1].qz : a.mats[2].qz);
         const half* scp = mi == 0 ? a.mats[0].sc : (mi == 1 ? a.mats[1].sc : a.mats[2].sc);
-        half* outp = mi == 0 ? a.mats[0].out : (mi == 1 ? a.mats[1].out : a.mats[2].out);
         const int N = mi == 0 ? a.mats[0].N : (mi == 1 ? a.mats[1].N : a.mats[2].N);
-        const int tile0 = mi == 0 ? a.mats[0].tile0 : (mi == 1 ? a.mats[1].tile0 : a.mats[2].tile0);
-        const int ctile = (EPI == GV_EPI_SILU_MUL) ? (tile >> 1) : (tile - tile0);
         const int col_tile0 = ctile * GV_TILE_N;
         const int tile_cols = min(GV_TILE_N, N - col_tile0);
         const bool col_ok = (wn * 32) < tile_cols;             // warp-uniform (N % 32 == 0)
@@ -272,75 +366,61 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const GemvArg
         #pragma unroll
         for (int j = 0; j < 4; j++) { A.cs[j] = 0.f; A.zs[j] = 0; A.zf[j] = 0; }
         A.cur_grp = -1;
-        const int xrow = min(g, M - 1);
 
-        for (int c0 = st0; c0 < st1; c0 += a.chunk_steps) {
-            const int c1 = min(st1, c0 + a.chunk_steps);
-            const int n = c1 - c0;
-            // this warp's unit of step c is k8-rows c * 8 + wk * 4 + [0, 4); drop the unit past K (K % 64 == 32)
-            int nw = n;
-            if ((c1 - 1) * 8 + wk * 4 + 4 > k8_lim) nw = n - 1;
-            const int g_lo = a.groups == 1 ? 0 : ((c0 * 2) >> a.gs_shift32);
-            const int g_hi = a.groups == 1 ? 0 : min(a.groups - 1, ((c1 * 2 - 1) >> a.gs_shift32));
+        for (int c0 = sg0; c0 < sg1; c0 += a.chunk_stages) {
+            const int c1 = min(sg1, c0 + a.chunk_stages);
+            const int g_lo = a.groups == 1 ? 0 : ((c0 * 4) >> a.gs_shift32);
+            const int g_hi = a.groups == 1 ? 0 : min(a.groups - 1, ((c1 * 4 - 1) >> a.gs_shift32));
 
-            __syncthreads();                 // previous chunk / segment finished with sc_s, zq_s, xs, red
-            // ---- scales / zeros of groups [g_lo, g_hi] for this tile's columns: TMA bulk copies onto s_bar ----
+            consumer_sync();                 // previous chunk / sub-tile finished with sc_s, zq_s, xs, red
+            // ---- scales / zeros of groups [g_lo, g_hi] for this tile's columns: TMA bulk copies onto sc_bar ----
             if (warp == 0) {
                 const int ng = g_hi - g_lo + 1;
                 const uint32_t sc_bytes = (uint32_t)tile_cols * 2, zq_bytes = (uint32_t)tile_cols / 2;
-                if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)ng * (sc_bytes + zq_bytes));
+                if (lane == 0) mbar_expect_tx(&sc_bar, (uint32_t)ng * (sc_bytes + zq_bytes));
                 __syncwarp();
                 for (int gi = lane; gi < ng; gi += 32) {
-                    bulk_g2s(sc_s + gi * SC_ROW, scp + (size_t)(g_lo + gi) * N + col_tile0, sc_bytes, &s_bar);
-                    bulk_g2s(zq_s + gi * ZQ_ROW, qz + (size_t)(g_lo + gi) * (N >> 3) + (col_tile0 >> 3), zq_bytes, &s_bar);
+                    bulk_g2s(sc_s + gi * SC_ROW, scp + (size_t)(g_lo + gi) * N + col_tile0, sc_bytes, &sc_bar);
+                    bulk_g2s(zq_s + gi * ZQ_ROW, qz + (size_t)(g_lo + gi) * (N >> 3) + (col_tile0 >> 3), zq_bytes, &sc_bar);
                 }
-            }
-            // ---- weight prefetch: the first U steps of this chunk (independent of the previous kernel) ----
-            const uint4* wp = reinterpret_cast<const uint4*>(qw + (size_t)(c0 * 8 + wk * 4 + t) * N + col_tile0 + lane_col);
-            const size_t wstep = (size_t)2 * N;          // uint4 per step (8 k8-rows)
-            uint4 wb[U];
-            #pragma unroll
-            for (int u = 0; u < U; u++) {
-                wb[u] = make_uint4(0, 0, 0, 0);
-                ldg_stream_v4_pred(wb[u], wp + (size_t)u * wstep, col_ok && u < nw && !(a.debug & 1));
             }
 
             if (!waited_dep) {
-                pdl_wait();                  // everything below may read x / write out and the shared workspace
+                pdl_wait();                  // everything below may read x / write out
                 waited_dep = true;
                 if (PRO == GV_PRO_RMSNORM) {
                     // row factor rm = half(rsqrt(mean(x^2) + eps))  (rms_norm.cu:20-79,113-116)
                     for (int m = 0; m < M; m++) {
                         float ss = 0.f;
                         const uint4* xr = reinterpret_cast<const uint4*>(a.x + (size_t)m * K);
-                        for (int i = tid; i < K / 8; i += THREADS) {
-                            uint4 v = xr[i];
-                            const half2* h = reinterpret_cast<const half2*>(&v);
+                        for (int i = tid; i < K / 8; i += CONSUMERS) {
+                            uint4 xv = xr[i];
+                            const half2* h = reinterpret_cast<const half2*>(&xv);
                             #pragma unroll
                             for (int j = 0; j < 4; j++) { float2 f = __half22float2(h[j]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
                         }
                         #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                         if (lane == 0) s_wsum[warp] = ss;
-                        __syncthreads();
+                        consumer_sync();
                         if (tid == 0) {
                             float tot = 0.f;
-                            for (int w = 0; w < THREADS / 32; w++) tot += s_wsum[w];
+                            for (int w = 0; w < CONSUMERS / 32; w++) tot += s_wsum[w];
                             s_rm[m] = __half2float(__float2half_rn(rsqrtf(tot * a.r_dim + a.eps)));
                         }
-                        __syncthreads();
+                        consumer_sync();
                     }
                 }
             }
 
-            // ---- stage x[:, c0*64 .. c1*64) into smem, permuted (0,4,1,5,2,6,3,7) inside each 8-block ----
+            // ---- stage x[:, c0*128 .. c1*128) into smem, permuted (0,4,1,5,2,6,3,7) inside each 8-block ----
             {
-                const int nk8 = n * (STEP_K / 8);
-                const int k8_0 = c0 * (STEP_K / 8);
-                for (int idx = tid; idx < M * nk8; idx += THREADS) {
+                const int nk8 = (c1 - c0) * STAGE_ROWS;
+                const int k8_0 = c0 * STAGE_ROWS;
+                for (int idx = tid; idx < M * nk8; idx += CONSUMERS) {
                     const int m = idx / nk8, j = idx - m * nk8;
                     const int k8 = k8_0 + j;
-                    uint4 v = make_uint4(0, 0, 0, 0);
+                    uint4 xv = make_uint4(0, 0, 0, 0);
                     if (k8 < k8_lim) {
                         const half* xr = a.x + (size_t)m * K;
                         if (a.x_map) {
@@ -348,15 +428,15 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const GemvArg
                             unsigned short h[8];
                             #pragma unroll
                             for (int i = 0; i < 8; i++) h[i] = __half_as_ushort(xr[mp[i]]);
-                            v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
-                            v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
+                            xv.x = h[0] | ((uint32_t)h[1] << 16); xv.y = h[2] | ((uint32_t)h[3] << 16);
+                            xv.z = h[4] | ((uint32_t)h[5] << 16); xv.w = h[6] | ((uint32_t)h[7] << 16);
                         } else {
-                            v = *reinterpret_cast<const uint4*>(xr + (size_t)k8 * 8);
+                            xv = *reinterpret_cast<const uint4*>(xr + (size_t)k8 * 8);
                         }
                         if (PRO == GV_PRO_RMSNORM) {
                             // (x * rm) * w with two fp16 multiplies, as rms_norm_kernel (rms_norm.cu:118-131)
                             const half2 rm2 = __float2half2_rn(s_rm[m]);
-                            half2* hv = reinterpret_cast<half2*>(&v);
+                            half2* hv = reinterpret_cast<half2*>(&xv);
                             if (a.x_map) {
                                 const uint32_t* mp = a.x_map + (size_t)k8 * 8;
                                 #pragma unroll
@@ -373,51 +453,70 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const GemvArg
                         }
                     }
                     uint4 o;
-                    o.x = __byte_perm(v.x, v.z, 0x5410);   // {h0, h4}
-                    o.y = __byte_perm(v.x, v.z, 0x7632);   // {h1, h5}
-                    o.z = __byte_perm(v.y, v.w, 0x5410);   // {h2, h6}
-                    o.w = __byte_perm(v.y, v.w, 0x7632);   // {h3, h7}
+                    o.x = __byte_perm(xv.x, xv.z, 0x5410);   // {h0, h4}
+                    o.y = __byte_perm(xv.x, xv.z, 0x7632);   // {h1, h5}
+                    o.z = __byte_perm(xv.y, xv.w, 0x5410);   // {h2, h6}
+                    o.w = __byte_perm(xv.y, xv.w, 0x7632);   // {h3, h7}
                     *reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)j * 16) = o;
                 }
             }
-            mbar_wait(&s_bar, bar_parity);   // scales / zeros landed
-            bar_parity ^= 1;
-            __syncthreads();                 // x staged
-
-            if (col_ok && !(a.debug & 1)) {
-                const unsigned char* xq = xs + (size_t)xrow * a.xs_stride + (size_t)(wk * 4 + t) * 16;   // + step * 128
-                const int ubase = c0 * 2 + wk;
-                const uint4* wq = wp + (size_t)U * wstep;
-                int i = 0;
-                const int nfull = (nw / U) * U;
-                for (; i < nfull; i += U) {
-                    #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const uint4 w = wb[u];
-                        ldg_stream_v4_pred(wb[u], wq + (size_t)(i + u) * wstep, (i + u + U) < nw);
-                        const int grp = (ubase + 2 * (i + u)) >> a.gs_shift32;
-                        if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_s, zq_s, lane_col);
-                        const uint4 xb = *reinterpret_cast<const uint4*>(xq + (size_t)(i + u) * 128);
-                        unit_mma(A, w, xb);
-                    }
-                }
+            mbar_wait(&sc_bar, sc_parity);   // scales / zeros landed
+            sc_parity ^= 1;
+            // expand the packed zeros into the per-column constants the unpack uses: half2(1024 + (z + 1))
+            for (int idx = tid; idx < (g_hi - g_lo + 1) * (GV_TILE_N / 8); idx += CONSUMERS) {
+                const int gi = idx >> 4, wd = idx & 15;
+                const uint32_t zw = *reinterpret_cast<const uint32_t*>(zq_s + gi * ZQ_ROW + wd * 4);
+                uint32_t o[8];
                 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    if (i + u < nw) {
-                        const int grp = (ubase + 2 * (i + u)) >> a.gs_shift32;
-                        if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_s, zq_s, lane_col);
-                        const uint4 xb = *reinterpret_cast<const uint4*>(xq + (size_t)(i + u) * 128);
-                        unit_mma(A, wb[u], xb);
-                    }
+                for (int j = 0; j < 8; j++) o[j] = (0x6401u + ((zw >> (4 * j)) & 0xfu)) * 0x00010001u;
+                uint4* dst = reinterpret_cast<uint4*>(zs_s + gi * ZS_ROW + wd * 32);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            consumer_sync();                 // x and zero constants staged
+
+            // Whole stages alternate between the two k-warps (stage j of this CTA goes to k-warp j & 1), so a warp
+            // sees 128 consecutive k per stage and switches quantisation group at most once per 4 units (gs >= 128).
+            // rows of this lane inside a stage: r = u*4 + t (u = 0..3); 16-byte chunk pg is stored at pg ^ (r & 7)
+            const uint32_t wa_even = smem_u32(ring) + wn * BOX_BYTES + t * 128 + ((pg ^ t) << 4);            // rows t, t+8
+            const uint32_t wa_odd = smem_u32(ring) + wn * BOX_BYTES + (t + 4) * 128 + ((pg ^ (t + 4)) << 4); // rows t+4, t+12
+            const uint32_t xa0 = smem_u32(xs) + (uint32_t)xrow * (uint32_t)a.xs_stride + (uint32_t)t * 16u;
+            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint32_t sc_a = smem_u32(sc_s), zs_a = smem_u32(zs_s);
+            const bool tail_checks = (K % STAGE_K) != 0;       // only a ragged last stage needs per-unit bounds checks
+            const bool skip_math = !col_ok || (a.debug & 5);
+            // first stage of this chunk that belongs to this k-warp: global stage counter parity == wk
+            int sg = c0 + ((wk - (jbase + (c0 - sg0))) & 1);
+            for (; sg < c1; sg += 2) {
+                const int j = jbase + (sg - sg0);                    // position in the ring sequence
+                const int slot = j % NST;
+                const uint32_t phase = (uint32_t)(j / NST) & 1u;
+                mbar_wait_a(full0 + slot * 8, phase);
+                if (!skip_math) {
+                    const uint32_t wb = slot * STAGE_BYTES;
+                    const uint32_t xb = xa0 + (uint32_t)(sg - c0) * (STAGE_ROWS * 16);
+                    const uint4 w0 = lds128(wa_even + wb), w1 = lds128(wa_odd + wb);
+                    const uint4 w2 = lds128(wa_even + wb + 8 * 128), w3 = lds128(wa_odd + wb + 8 * 128);
+                    const uint4 x0 = lds128(xb), x1 = lds128(xb + 64), x2 = lds128(xb + 128), x3 = lds128(xb + 192);
+                    const int u0 = sg * 4;
+                    #define GV_UNIT(U_, W_, X_)                                                            \
+                        if (!tail_checks || ((u0 + U_) * 4 + 4) <= k8_lim) {                               \
+                            const int grp = (u0 + U_) >> a.gs_shift32;                                     \
+                            if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zs_a, lane_col);        \
+                            unit_mma(A, W_, X_, a.debug);                                                  \
+                        }
+                    GV_UNIT(0, w0, x0) GV_UNIT(1, w1, x1) GV_UNIT(2, w2, x2) GV_UNIT(3, w3, x3)
+                    #undef GV_UNIT
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty0 + slot * 8);
             }
         }
+        jbase += sg1 - sg0;
         if (A.cur_grp >= 0) {
             #pragma unroll
             for (int j = 0; j < 8; j++) A.acc[j] = fmaf(A.cs[j >> 1], A.cg[j], A.acc[j]);
         }
-        const bool last_segment = (s + (st1 - st0)) >= S1;
-        if (last_segment) pdl_launch_dependents();       // this CTA has issued all its weight loads
 
         // ---- reduce the WK k-warps through shared memory: red[wk][m][col] ----
         {
@@ -429,11 +528,7 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const GemvArg
                 r[(2 * t + 1) * RED_LD + lane_col + j] = A.acc[2 * j + 1];
             }
         }
-        __syncthreads();
-
-        const int ecol = tid & (GV_TILE_N - 1);
-        const int em0 = tid >> 7;                 // 0 or 1; this thread owns rows em0, em0+2, em0+4, em0+6
-        float v[4];
+        consumer_sync();
         #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int m = em0 + 2 * i;
@@ -443,160 +538,126 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const GemvArg
             v[i] = sum;
         }
 
-        bool finalize = true;
-        const bool full = (st0 == 0 && st1 == spt) || (a.debug & 2);
-        if (!full) {
-            // stream-K fix-up: publish the partial, last CTA to arrive sums all partials of the tile in CTA order
-            const long long tstart = (long long)tile * spt, tend = tstart + spt - 1;
-            const int c_first = (int)(((tstart + 1) * G - 1) / a.total_steps);
-            const int c_last = (int)(((tend + 1) * G - 1) / a.total_steps);
-            const int my_first_tile = (int)(S0 / spt);
-            const int slot = blockIdx.x * 2 + (tile != my_first_tile ? 1 : 0);
-            float* pp = a.partials + (size_t)slot * GV_MAXM * GV_TILE_N;
+        if (cs > 1) {
+            // ---- cluster split-K: deposit the partial in the leader's slot [sub][rank] through DSMEM ----
+            cluster_wait();                                   // barrier #sub complete: leader is up / previous slots consumed
+            if (NSUB == 2 && sub == 1 && rank == 0) sum_slots(0, vprev);
+            const uint32_t dst = mapa_shared(smem_u32(slots + ((size_t)(sub * cs + rank) * M) * GV_TILE_N), 0);
             #pragma unroll
-            for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) pp[m * GV_TILE_N + ecol] = v[i]; }
-            __syncthreads();
-            if (tid == 0) s_old = atom_add_acq_rel(&a.counters[tile], 1u);    // release our partial / acquire the others'
-            __syncthreads();
-            finalize = (s_old == (unsigned)(c_last - c_first));
-            if (finalize) {
-                #pragma unroll
-                for (int i = 0; i < 4; i++) v[i] = 0.f;
-                // only c_first can contribute its *second* slot (when it started in an earlier tile)
-                const long long start_first = (long long)c_first * a.total_steps / G;
-                const int first_par = (start_first < tstart) ? 1 : 0;
-                for (int cb = c_first; cb <= c_last; cb += 8) {
-                    float pv[8][4];
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int c = cb + j;
-                        const float* qp = a.partials + (size_t)(c * 2 + (c == c_first ? first_par : 0)) * GV_MAXM * GV_TILE_N;
-                        #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int m = em0 + 2 * i;
-                            pv[j][i] = (c <= c_last && m < M) ? ldcg_f32(qp + m * GV_TILE_N + ecol) : 0.f;
-                        }
-                    }
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        #pragma unroll
-                        for (int i = 0; i < 4; i++) v[i] += pv[j][i];
-                }
-                if (tid == 0) a.counters[tile] = 0u;     // ready for the next launch (stream-ordered)
-            }
+            for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) st_cluster_f32(dst + (uint32_t)(m * GV_TILE_N + ecol) * 4u, v[i]); }
+            cluster_arrive();                                 // release
+        } else if (NSUB == 2 && sub == 0) {
+            #pragma unroll
+            for (int i = 0; i < 4; i++) vprev[i] = v[i];
         }
+    }
+    if (cs > 1) {
+        cluster_wait();                                       // acquire: all partials of the last sub-tile are in our smem
+        if (rank != 0) return;
+        sum_slots(NSUB - 1, v);
+    }
 
-        if (finalize) {
-            const int col = col_tile0 + ecol;
-            if (EPI == GV_EPI_STORE) {
-                if (col < N) {
-                    #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int m = em0 + 2 * i;
-                        if (m < M) {
-                            float r = v[i];
-                            half* o = outp + (size_t)m * N + col;
-                            if (a.no_zero) r += __half2float(*o);
-                            *o = __float2half_rn(r);
-                        }
-                    }
-                }
-            } else if (EPI == GV_EPI_ROPE_CACHE) {
-                // tile == one head (head_dim == 128): rope on q / k (rope.cu:48-67), k/v written to the cache
-                // (q4_attn.cu:32-51).  Rows are q_len tokens of one sequence (decode path, model.py:528).
-                __syncthreads();
-                half* hs = reinterpret_cast<half*>(red);          // [m][128]
-                #pragma unroll
-                for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) hs[m * GV_TILE_N + ecol] = __float2half_rn(v[i]); }
-                __syncthreads();
-                const int head = col_tile0 / GV_TILE_N;
+    // ================================== epilogue (leader CTA, consumer warps) ==================================
+    {
+        half* outp = mi == 0 ? a.mats[0].out : (mi == 1 ? a.mats[1].out : a.mats[2].out);
+        const int N = mi == 0 ? a.mats[0].N : (mi == 1 ? a.mats[1].N : a.mats[2].N);
+        const int col_tile0 = ctile * GV_TILE_N;
+        const int col = col_tile0 + ecol;
+        if (EPI == GV_EPI_STORE) {
+            if (col < N) {
                 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int m = em0 + 2 * i;
-                    if (m < M && col < N) {
-                        half val = hs[m * GV_TILE_N + ecol];
-                        if (mi < 2) {
-                            const int pos = a.past_len + m;
-                            const half* sr = a.sin + (size_t)pos * GV_TILE_N;
-                            const half* cr = a.cos + (size_t)pos * GV_TILE_N;
-                            const half other = hs[m * GV_TILE_N + (ecol ^ 64)];
-                            if (ecol < 64) val = __hfma(val, cr[ecol], __hmul(other, __hneg(sr[ecol])));
-                            else           val = __hfma(val, cr[ecol], __hmul(other, sr[ecol]));
-                        }
-                        outp[(size_t)m * N + col] = val;
-                        if (mi >= 1) {
-                            half* cache = mi == 1 ? a.key_cache : a.value_cache;
-                            cache[((size_t)head * a.max_seq_len + a.past_len + m) * GV_TILE_N + ecol] = val;
-                        }
+                    if (m < M) {
+                        float r = v[i];
+                        half* o = outp + (size_t)m * N + col;
+                        if (a.no_zero) r += __half2float(*o);
+                        *o = __float2half_rn(r);
                     }
                 }
-            } else if (EPI == GV_EPI_SILU_MUL) {
-                // mats = {gate, up}: tiles alternate gate_j, up_j.  Whichever of the pair finishes second
-                // combines silu(gate) * up (q4_mlp.cu:27-36,46-88) and writes mats[0].out.
-                const int pair = ctile;
-                float* stg = a.pair_stage + ((size_t)pair * 2 + mi) * GV_MAXM * GV_TILE_N;
-                #pragma unroll
-                for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) stg[m * GV_TILE_N + ecol] = v[i]; }
-                __syncthreads();
-                if (tid == 0) s_old = atom_add_acq_rel(&a.pair_counters[pair], 1u);
-                __syncthreads();
-                if (s_old == 1u) {
-                    const float* og = a.pair_stage + ((size_t)pair * 2 + 0) * GV_MAXM * GV_TILE_N;
-                    const float* ou = a.pair_stage + ((size_t)pair * 2 + 1) * GV_MAXM * GV_TILE_N;
-                    if (col < N) {
-                        #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int m = em0 + 2 * i;
-                            if (m < M) {
-                                const half gt = __float2half_rn(ldcg_f32(og + m * GV_TILE_N + ecol));
-                                const half up = __float2half_rn(ldcg_f32(ou + m * GV_TILE_N + ecol));
-                                a.mats[0].out[(size_t)m * N + col] = __hmul(silu_h(gt), up);
-                            }
-                        }
+            }
+        } else if (EPI == GV_EPI_ROPE_CACHE) {
+            // tile == one head (head_dim == 128): rope on q / k (rope.cu:48-67), k/v written to the cache
+            // (q4_attn.cu:32-51).  Rows are q_len tokens of one sequence (decode path, model.py:528).
+            consumer_sync();
+            half* hs = reinterpret_cast<half*>(red);          // [m][128]
+            #pragma unroll
+            for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) hs[m * GV_TILE_N + ecol] = __float2half_rn(v[i]); }
+            consumer_sync();
+            const int head = col_tile0 / GV_TILE_N;
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int m = em0 + 2 * i;
+                if (m < M && col < N) {
+                    half val = hs[m * GV_TILE_N + ecol];
+                    if (mi < 2) {
+                        const int pos = a.past_len + m;
+                        const half* sr = a.sin + (size_t)pos * GV_TILE_N;
+                        const half* cr = a.cos + (size_t)pos * GV_TILE_N;
+                        const half other = hs[m * GV_TILE_N + (ecol ^ 64)];
+                        if (ecol < 64) val = __hfma(val, cr[ecol], __hmul(other, __hneg(sr[ecol])));
+                        else           val = __hfma(val, cr[ecol], __hmul(other, sr[ecol]));
                     }
-                    if (tid == 0) a.pair_counters[pair] = 0u;
+                    outp[(size_t)m * N + col] = val;
+                    if (mi >= 1) {
+                        half* cache = mi == 1 ? a.key_cache : a.value_cache;
+                        cache[((size_t)head * a.max_seq_len + a.past_len + m) * GV_TILE_N + ecol] = val;
+                    }
+                }
+            }
+        } else if (EPI == GV_EPI_SILU_MUL) {
+            // vprev = gate tile, v = up tile (both fully reduced): silu(gate) * up in fp16 (q4_mlp.cu:27-36,46-88)
+            if (col < N) {
+                #pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int m = em0 + 2 * i;
+                    if (m < M) a.mats[0].out[(size_t)m * N + col] = __hmul(silu_h(__float2half_rn(vprev[i])), __float2half_rn(v[i]));
                 }
             }
         }
-        s += st1 - st0;
     }
 }
 
 template <int PRO, int EPI>
-int launch_cfg(ExlDevice* ds, const GemvArgs& a, size_t smem, cudaStream_t stream)
+int launch_cfg(ExlDevice* ds, GemvArgs& a, int items, cudaStream_t stream)
 {
     auto kern = q4_gemv_kernel<PRO, EPI>;
-    static int ctas_per_sm_cache[GV_MAXM + 1] = {0};
-    static size_t smem_cache[GV_MAXM + 1] = {0};
     static int attr_device_done[EXL_MAX_DEVICES] = {0};
-    static int use_pdl = -1;
+    static int use_pdl = -1, force_cs = -1;
     if (use_pdl < 0) { const char* e = getenv("EXL_GV_PDL"); use_pdl = e ? atoi(e) : 1; }
+    if (force_cs < 0) { const char* e = getenv("EXL_GV_CS"); force_cs = e ? atoi(e) : 0; }
     if (!attr_device_done[ds->device]) {
         EXL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_device_done[ds->device] = 1;
     }
-    if (smem_cache[a.M] != smem || ctas_per_sm_cache[a.M] == 0) {
-        int nb = 0;
-        EXL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem));
-        if (nb < 1) return exl_set_err(EXL_ERR_CUDA, "q4_gemv: kernel does not fit (smem %zu)", smem);
-        ctas_per_sm_cache[a.M] = nb; smem_cache[a.M] = smem;
-    }
-    int cps = ctas_per_sm_cache[a.M];
-    if (const char* e = getenv("EXL_GV_CPS")) { int v = atoi(e); if (v >= 1 && v < cps) cps = v; }
-    long long grid = (long long)ds->num_sms * cps;
-    if (grid > a.total_steps) grid = a.total_steps;
-    if (grid > GV_MAX_CTAS) grid = GV_MAX_CTAS;
+    // K split factor == cluster size: as large as keeps every CTA of the launch co-resident (2 CTAs / SM)
+    const int cap = ds->num_sms * 2;
+    int cs = MAX_CS;
+    while (cs > 1 && ((long long)items * cs > cap || cs > a.spt || 2 * cs * a.M * GV_TILE_N * (int)sizeof(float) > SLOT_BUDGET)) cs >>= 1;
+    if (force_cs >= 1 && force_cs <= MAX_CS && force_cs <= a.spt && 2 * force_cs * a.M * GV_TILE_N * (int)sizeof(float) <= SLOT_BUDGET) cs = force_cs;
+    a.cs = cs;
+    const size_t smem = 1024 + (size_t)NST * STAGE_BYTES + (size_t)GMAXC * (SC_ROW + ZQ_ROW + ZS_ROW) + (size_t)WK * GV_MAXM * RED_LD * sizeof(float) +
+                        (size_t)2 * cs * a.M * GV_TILE_N * sizeof(float) + (size_t)a.M * a.xs_stride;
 
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.gridDim = dim3((unsigned)(items * cs)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (cs > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cs; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (e != cudaSuccess) return exl_set_err(EXL_ERR_CUDA, "launch of q4_gemv_kernel failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return exl_set_err(EXL_ERR_CUDA, "launch of q4_gemv_kernel failed: %s (items %d, cs %d, smem %zu)", cudaGetErrorString(e), items, cs, smem);
     return EXL_OK;
 }
 
@@ -617,37 +678,35 @@ int exl_gemv_launch(ExlDevice* ds, const half* x, int M, const exl_q4_matrix* co
         return exl_set_err(EXL_ERR_ARG, "q4_gemv: groupsize=%d must be 32 * 2^n", w0->groupsize);
     int sh = 0; while ((1 << sh) < gs32) sh++;
     a.gs_shift32 = w0->groups == 1 ? 30 : sh;
-    a.spt = (w0->K + STEP_K - 1) / STEP_K;
+    a.spt = (w0->K + STAGE_K - 1) / STAGE_K;
     int tiles = 0;
     for (int i = 0; i < num_mats; i++) {
         const exl_q4_matrix* w = mats[i];
         if (w->K != w0->K || w->groups != w0->groups || w->x_map != w0->x_map)
             return exl_set_err(EXL_ERR_ARG, "q4_gemv: fused matrices must share K, groups and x_map");
         if (w->N % 32 != 0) return exl_set_err(EXL_ERR_ARG, "q4_gemv: N=%d must be a multiple of 32", w->N);
+        a.tmaps[i] = w->tmap_w;
         a.mats[i].qw = w->qweight; a.mats[i].qz = w->qzeros; a.mats[i].sc = w->scales; a.mats[i].out = outs[i];
         a.mats[i].N = w->N; a.mats[i].tile0 = tiles;
         tiles += (w->N + GV_TILE_N - 1) / GV_TILE_N;
     }
+    int items = tiles;
     if (epilogue == GV_EPI_SILU_MUL) {
-        // gate/up tiles are interleaved (g0,u0,g1,u1,...) so the two halves of a pair finish close together
+        // one cluster computes the gate tile and then the up tile of the same columns and combines them in registers
         if (num_mats != 2 || mats[0]->N != mats[1]->N)
             return exl_set_err(EXL_ERR_ARG, "q4_gemv: SILU_MUL epilogue needs {gate, up} of equal width");
-        if (tiles / 2 > GV_MAX_PAIRS) return exl_set_err(EXL_ERR_ARG, "q4_gemv: too many gate/up tiles");
-        a.pair_stage = ds->gemv_pair_stage; a.pair_counters = ds->gemv_pair_counters;
+        items = tiles / 2;
     }
-    if (tiles > GV_MAX_TILES) return exl_set_err(EXL_ERR_ARG, "q4_gemv: too many tiles (%d)", tiles);
-    a.num_mats = num_mats; a.total_tiles = tiles; a.total_steps = (long long)tiles * a.spt;
+    a.num_mats = num_mats;
     a.no_zero = no_zero ? 1 : 0;
-    // staging chunk: M * chunk_k * 2 bytes of x <= 32 KB, and at most GMAXC quantisation groups
-    int chunk_k = (32 * 1024) / (2 * M);
+    // staging chunk: M * chunk_k * 2 bytes of x <= XS_BUDGET, and at most GMAXC quantisation groups
+    int chunk_k = XS_BUDGET / (2 * M);
     if (w0->groups > 1) { int gk = (GMAXC - 1) * w0->groupsize; if (gk < chunk_k) chunk_k = gk; }
-    chunk_k = (chunk_k / STEP_K) * STEP_K;
-    int chunk_steps = chunk_k / STEP_K;
-    if (chunk_steps < 1) return exl_set_err(EXL_ERR_ARG, "q4_gemv: cannot stage a chunk (groupsize %d)", w0->groupsize);
-    if (chunk_steps > a.spt) chunk_steps = a.spt;
-    a.chunk_steps = chunk_steps;
-    a.xs_stride = chunk_steps * STEP_K * 2 + 64;
-    a.partials = ds->gemv_partials; a.counters = ds->gemv_counters;
+    int chunk_stages = chunk_k / STAGE_K;
+    if (chunk_stages < 1) return exl_set_err(EXL_ERR_ARG, "q4_gemv: cannot stage a chunk (groupsize %d)", w0->groupsize);
+    if (chunk_stages > a.spt) chunk_stages = a.spt;
+    a.chunk_stages = chunk_stages;
+    a.xs_stride = chunk_stages * STAGE_K * 2 + 64;
     if (const char* e = getenv("EXL_GV_DEBUG")) a.debug = atoi(e);
     if (fused) {
         a.norm_w = fused->norm_w; a.eps = fused->eps; a.r_dim = 1.0f / (float)w0->K;
@@ -655,15 +714,14 @@ int exl_gemv_launch(ExlDevice* ds, const half* x, int M, const exl_q4_matrix* co
         a.num_kv_heads = fused->num_kv_heads; a.past_len = fused->past_len; a.max_seq_len = fused->max_seq_len;
         a.key_cache = fused->key_cache; a.value_cache = fused->value_cache;
     }
-    size_t smem = (size_t)GMAXC * (SC_ROW + ZQ_ROW) + (size_t)WK * GV_MAXM * RED_LD * sizeof(float) + (size_t)M * a.xs_stride;
 
-    if (prologue == GV_PRO_PLAIN && epilogue == GV_EPI_STORE) return launch_cfg<GV_PRO_PLAIN, GV_EPI_STORE>(ds, a, smem, stream);
-    if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_STORE) return launch_cfg<GV_PRO_RMSNORM, GV_EPI_STORE>(ds, a, smem, stream);
+    if (prologue == GV_PRO_PLAIN && epilogue == GV_EPI_STORE) return launch_cfg<GV_PRO_PLAIN, GV_EPI_STORE>(ds, a, items, stream);
+    if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_STORE) return launch_cfg<GV_PRO_RMSNORM, GV_EPI_STORE>(ds, a, items, stream);
     if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_ROPE_CACHE) {
         if (!fused || fused->head_dim != GV_TILE_N) return exl_set_err(EXL_ERR_ARG, "q4_gemv: rope epilogue needs head_dim == 128");
-        return launch_cfg<GV_PRO_RMSNORM, GV_EPI_ROPE_CACHE>(ds, a, smem, stream);
+        return launch_cfg<GV_PRO_RMSNORM, GV_EPI_ROPE_CACHE>(ds, a, items, stream);
     }
-    if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_SILU_MUL) return launch_cfg<GV_PRO_RMSNORM, GV_EPI_SILU_MUL>(ds, a, smem, stream);
-    if (prologue == GV_PRO_PLAIN && epilogue == GV_EPI_SILU_MUL) return launch_cfg<GV_PRO_PLAIN, GV_EPI_SILU_MUL>(ds, a, smem, stream);
+    if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_SILU_MUL) return launch_cfg<GV_PRO_RMSNORM, GV_EPI_SILU_MUL>(ds, a, items, stream);
+    if (prologue == GV_PRO_PLAIN && epilogue == GV_EPI_SILU_MUL) return launch_cfg<GV_PRO_PLAIN, GV_EPI_SILU_MUL>(ds, a, items, stream);
     return exl_set_err(EXL_ERR_ARG, "q4_gemv: unsupported prologue/epilogue combination %d/%d", prologue, epilogue);
 }

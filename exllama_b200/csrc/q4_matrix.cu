@@ -55,6 +55,32 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const uint32_t* __rest
 
 } // namespace
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+int exl_encode_weight_tmap(exl_q4_matrix* w)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)w->N, (cuuint64_t)(w->K / 8)};
+    const cuuint64_t strides[1] = {(cuuint64_t)w->N * 4};              // bytes between k8-rows
+    const cuuint32_t box[2] = {32, 16};                                // 32 columns (128 B) x 16 k8-rows
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&w->tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)w->qweight, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for K=%d N=%d", (int)r, w->K, w->N);
+    return EXL_OK;
+}
+
 int exl_make_sequential_launch(uint32_t* qweight, uint32_t* tmp, const uint32_t* x_map, int K, int N, cudaStream_t stream)
 {
     dim3 block(256), grid((N / 4 + 255) / 256, K / 8);
