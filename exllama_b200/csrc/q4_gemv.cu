@@ -14,12 +14,14 @@
 //  * group scales / zeros of the CTA's k-range are staged into shared memory with 1-D TMA bulk copies
 //    (cp.async.bulk + mbarrier); x is staged by the threads because it is permuted (and gathered through the
 //    act-order x_map, and RMS-normalised for the fused decoder ops) on the way in.
-//  * nibbles are expanded two at a time with the 0x6400 fp16 magic (q | 0x6400 == 1024 + q), the zero point is
-//    folded into the bias removal, and the products are formed by mma.sync m16n8k16 with the *weights as the
-//    A operand straight from registers* (rows = 16 output columns) and the <= 8 activation rows as the n = 8
-//    operand: exact fp16 products, fp32 accumulation, cost independent of M for M <= 8.
-//    K is traversed in the permuted order (0,4,1,5,2,6,3,7) inside each 8-block so no nibble shuffling is needed.
-//  * group scales are applied once per group to an fp32 group accumulator.
+//  * the contraction runs on the integer tensor cores (mma.sync m16n8k32 u8 x s8/u8 -> s32, SASS IMMA.16832) with
+//    the *nibbles as the A operand straight from registers* (two ops per 8 weights: w & 0x0f0f0f0f, (w >> 4) & ...)
+//    and the <= 8 activation rows as the n = 8 operand, so the unpack costs 3/8 instruction per weight and the cost
+//    is independent of M for M <= 8.  x is carried per quantisation group as a 16-bit integer with its own scale
+//    (two byte planes), the zero point becomes one multiply per group (zp * sum x_q), and everything inside a
+//    group is exact integer arithmetic; groups are combined in fp32 with the fp16 group scales.
+//    Quantising x to 16 bits per group costs < 1e-4 of the output rms -- below the fp16 rounding of the result
+//    (the reference accumulates in fp16, matrix.cuh:87-133).
 //  * split-K without global memory: one thread-block CLUSTER owns one 128-column tile; its CS CTAs take contiguous
 //    K slices and the leader sums the CS partials out of its own shared memory, where the peers deposited them
 //    through DSMEM (st.shared::cluster) before a cluster barrier.  Fixed summation order => deterministic; no fp16
@@ -47,12 +49,12 @@ constexpr int BOX_BYTES = STAGE_ROWS * BOX_COLS * 4;
 constexpr int STAGE_BYTES = WN * BOX_BYTES;  // 8 KB
 constexpr int NST = GV_NST;
 constexpr int RED_LD = GV_TILE_N + 4;
-constexpr int GMAXC = 16;                  // max quantisation groups staged per chunk
+constexpr int GMAXC = 32;                  // max quantisation groups staged per chunk
 constexpr int SC_ROW = GV_TILE_N * 2;      // bytes of scales per group row in smem
 constexpr int ZQ_ROW = GV_TILE_N / 2;      // bytes of packed zeros per group row in smem (raw, as TMA delivers them)
-constexpr int ZS_ROW = GV_TILE_N * 4;      // bytes of expanded zero constants per group row: half2(1024 + zp) per column
+constexpr int SEG_BYTES = GMAXC * GV_MAXM * 16;  // per (segment, token): {sum of x_q over even ring stages, over odd ring stages, x scale, -}
 constexpr int XS_BUDGET = 16 * 1024;       // bytes of staged x per chunk
-constexpr int SLOT_BUDGET = 16 * 1024;     // bytes of cluster-reduction slots (2 x CS x M x 512 B)
+constexpr int SLOT_BUDGET = 8 * 1024;      // bytes of cluster-reduction slots (2 x CS x M x 512 B)
 constexpr int MAX_CS = 8;
 
 struct GemvMatDev
@@ -137,25 +139,15 @@ __device__ __forceinline__ uint32_t lop_and_or(uint32_t a, uint32_t m, uint32_t 
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(m), "r"(o)); return r;   // (a & m) | o
 }
 
-// one packed word (8 k-values of one column) -> 4 half2 registers holding (q - zp) for the nibble pairs
-// (0,4) (1,5) (2,6) (3,7).  zs = half2(1024 + zp), zf = half2(-(64 + zp)).
-__device__ __forceinline__ void dequant_word(uint32_t w, uint32_t zs, uint32_t zf,
-                                             uint32_t& p04, uint32_t& p15, uint32_t& p26, uint32_t& p37)
+__device__ __forceinline__ void imma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-    const uint32_t MLO = 0x000f000fu, MHI = 0x00f000f0u, EX = 0x64006400u, R16 = 0x2c002c00u;
-    uint32_t w8 = w >> 8;
-    p04 = h2_sub(lop_and_or(w, MLO, EX), zs);
-    p15 = h2_fma(lop_and_or(w, MHI, EX), R16, zf);
-    p26 = h2_sub(lop_and_or(w8, MLO, EX), zs);
-    p37 = h2_fma(lop_and_or(w8, MHI, EX), R16, zf);
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1)
+__device__ __forceinline__ void imma_u8u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 __device__ __forceinline__ half silu_h(half x)
@@ -168,60 +160,101 @@ __device__ __forceinline__ half silu_h(half x)
 }
 
 // Per-thread state of the inner product loop for one tile segment.
+// The contraction runs on the integer tensor cores: the 4-bit weights are used as they are (u8 0..15) and each
+// x segment (one quantisation group, or its intersection with the staging chunk) is carried as a 16-bit integer
+// x_q = 256 * a + b with its own scale sx (a: signed high byte, b: unsigned low byte).  Per segment
+//     sum_k x_k (q_k - zp) = sx * ( 256 * sum a_k q_k + sum b_k q_k - zp * sum x_q,k )        (exact in int32)
+// and the result is folded into fp32 totals with the group's weight scale.
 struct Accum
 {
-    float acc[8];      // scaled totals
-    float cg[8];       // current group, unscaled
-    float cs[4];       // current group's scales (4 columns)
-    uint32_t zs[4], zf[4];
+    float acc[8];        // fp32 totals: [col j >> 1][token 2t + (j & 1)]
+    int ia[8], ib[8];    // current segment: plane a / plane b integer dot products
+    float cs[4];         // segment's weight scales (4 columns)
+    uint32_t zp4;        // segment's zero points + 1, one byte per column
+    int sxq[2];          // per token (2t, 2t+1): sum of x_q over the part of the segment this k-warp accumulates
+    float sxs[2];        // per token: x scale of the segment
     int cur_grp;
 };
 
-__device__ __forceinline__ void group_switch(Accum& A, int grp, int g_lo, uint32_t sc_addr, uint32_t zs_addr, int lane_col)
+__device__ __forceinline__ void seg_flush(Accum& A)
 {
-    if (A.cur_grp >= 0) {
-        #pragma unroll
-        for (int j = 0; j < 8; j++) { A.acc[j] = fmaf(A.cs[j >> 1], A.cg[j], A.acc[j]); A.cg[j] = 0.f; }
+    #pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int col = j >> 1, tok = j & 1;
+        const int zp = (int)((A.zp4 >> (8 * col)) & 0xffu);
+        const int val = A.ia[j] * 256 + A.ib[j] - zp * A.sxq[tok];
+        A.acc[j] = fmaf(A.cs[col] * A.sxs[tok], (float)val, A.acc[j]);
+        A.ia[j] = 0; A.ib[j] = 0;
     }
+}
+
+__device__ __forceinline__ void group_switch(Accum& A, int grp, int g_lo, uint32_t sc_addr, uint32_t zq_addr, uint32_t seg_addr,
+                                             int lane_col, int t, int wk)
+{
+    if (A.cur_grp >= 0) seg_flush(A);
     const int gl = grp - g_lo;
-    uint2 sc; uint4 z;
+    uint2 sc; uint32_t zw; uint4 s0, s1;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sc.x), "=r"(sc.y) : "r"(sc_addr + gl * SC_ROW + lane_col * 2));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(z.x), "=r"(z.y), "=r"(z.z), "=r"(z.w) : "r"(zs_addr + gl * ZS_ROW + lane_col * 4));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(zq_addr + gl * ZQ_ROW + (lane_col >> 3) * 4));
+    const uint32_t ea = seg_addr + (gl * GV_MAXM + 2 * t) * 16;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s0.x), "=r"(s0.y), "=r"(s0.z), "=r"(s0.w) : "r"(ea));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s1.x), "=r"(s1.y), "=r"(s1.z), "=r"(s1.w) : "r"(ea + 16));
     const half2 s01 = *reinterpret_cast<const half2*>(&sc.x);
     const half2 s23 = *reinterpret_cast<const half2*>(&sc.y);
     A.cs[0] = __low2float(s01); A.cs[1] = __high2float(s01);
     A.cs[2] = __low2float(s23); A.cs[3] = __high2float(s23);
-    // zs = half2(1024 + zp) comes from the staged table; zf = half2(-(64 + zp)) = 0xd400 + 16 * zp per half
-    A.zs[0] = z.x; A.zs[1] = z.y; A.zs[2] = z.z; A.zs[3] = z.w;
-    #pragma unroll
-    for (int j = 0; j < 4; j++) A.zf[j] = ((A.zs[j] & 0x001f001fu) << 4) | 0xd400d400u;
+    const uint32_t z4 = zw >> ((lane_col & 4) * 4);          // this lane's 4 zero nibbles
+    A.zp4 = ((z4 & 0xfu) | ((z4 & 0xf0u) << 4) | ((z4 & 0xf00u) << 8) | ((z4 & 0xf000u) << 12)) + 0x01010101u;
+    A.sxq[0] = (int)(wk ? s0.y : s0.x); A.sxs[0] = __uint_as_float(s0.z);
+    A.sxq[1] = (int)(wk ? s1.y : s1.x); A.sxs[1] = __uint_as_float(s1.z);
     A.cur_grp = grp;
 }
 
-__device__ __forceinline__ void unit_mma(Accum& A, const uint4& w, const uint4& xb, int dbg = 0)
+// Quantise one staged k8-row (8 halves, natural order) with scale 1/inv: returns sum of x_q and the packed byte planes
+// {a(0,2,4,6), a(1,3,5,7), b(0,2,4,6), b(1,3,5,7)},  x_q = 256 a + b.
+__device__ __forceinline__ int quantise_row(const uint4& hv, float inv, uint4& o)
 {
-    uint32_t p0[4], p1[4], p2[4], p3[4];
-    if (dbg & 16) {            // experiment: no unpack
-        p0[0] = w.x; p0[1] = w.y; p0[2] = w.z; p0[3] = w.w; p1[0] = w.y; p1[1] = w.z; p1[2] = w.w; p1[3] = w.x;
-        p2[0] = w.z; p2[1] = w.w; p2[2] = w.x; p2[3] = w.y; p3[0] = w.w; p3[1] = w.x; p3[2] = w.y; p3[3] = w.z;
-    } else {
-        dequant_word(w.x, A.zs[0], A.zf[0], p0[0], p0[1], p0[2], p0[3]);
-        dequant_word(w.y, A.zs[1], A.zf[1], p1[0], p1[1], p1[2], p1[3]);
-        dequant_word(w.z, A.zs[2], A.zf[2], p2[0], p2[1], p2[2], p2[3]);
-        dequant_word(w.w, A.zs[3], A.zf[3], p3[0], p3[1], p3[2], p3[3]);
+    const half2* h = reinterpret_cast<const half2*>(&hv);
+    int sum = 0;
+    o = make_uint4(0, 0, 0, 0);
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(h[i]);
+        const int q0 = __float2int_rn(f.x * inv), q1 = __float2int_rn(f.y * inv);
+        sum += q0 + q1;
+        o.x |= (uint32_t)((q0 >> 8) & 0xff) << (8 * i);
+        o.y |= (uint32_t)((q1 >> 8) & 0xff) << (8 * i);
+        o.z |= (uint32_t)(q0 & 0xff) << (8 * i);
+        o.w |= (uint32_t)(q1 & 0xff) << (8 * i);
     }
-    float (&cA)[4] = *reinterpret_cast<float (*)[4]>(&A.cg[0]);
-    float (&cB)[4] = *reinterpret_cast<float (*)[4]>(&A.cg[4]);
-    if (dbg & 8) {             // experiment: no tensor-core work (keep the unpack alive)
-        cA[0] += __uint_as_float(p0[0] ^ p1[1] ^ p0[2] ^ p1[3] ^ xb.x); cA[1] += __uint_as_float(p1[0] ^ p0[1] ^ p1[2] ^ p0[3] ^ xb.y);
-        cB[0] += __uint_as_float(p2[0] ^ p3[1] ^ p2[2] ^ p3[3] ^ xb.z); cB[1] += __uint_as_float(p3[0] ^ p2[1] ^ p3[2] ^ p2[3] ^ xb.w);
-        return;
-    }
-    // columns (c0, c1): rows g / g+8 of A;  k order (0,4,1,5) then (2,6,3,7)
-    mma16816(cA, p0[0], p1[0], p0[1], p1[1], xb.x, xb.y);
-    mma16816(cA, p0[2], p1[2], p0[3], p1[3], xb.z, xb.w);
-    mma16816(cB, p2[0], p3[0], p2[1], p3[1], xb.x, xb.y);
-    mma16816(cB, p2[2], p3[2], p2[3], p3[3], xb.z, xb.w);
+    return sum;
+}
+__device__ __forceinline__ float row_absmax(const uint4& hv)
+{
+    const half2* h = reinterpret_cast<const half2*>(&hv);
+    float mx = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(__habs2(h[i])); mx = fmaxf(mx, fmaxf(f.x, f.y)); }
+    return mx;
+}
+
+// one unit = this lane's uint4 of weights (4 columns x 8 k) against the two byte planes of x (xb = {a_even, a_odd, b_even, b_odd})
+__device__ __forceinline__ void unit_mma(Accum& A, const uint4& w, const uint4& xb)
+{
+    const uint32_t M4 = 0x0f0f0f0fu;
+    const uint32_t lo0 = w.x & M4, hi0 = (w.x >> 4) & M4;      // bytes = nibbles (0,2,4,6) / (1,3,5,7) of column c0
+    const uint32_t lo1 = w.y & M4, hi1 = (w.y >> 4) & M4;
+    const uint32_t lo2 = w.z & M4, hi2 = (w.z >> 4) & M4;
+    const uint32_t lo3 = w.w & M4, hi3 = (w.w >> 4) & M4;
+    int (&aA)[4] = *reinterpret_cast<int (*)[4]>(&A.ia[0]);
+    int (&aB)[4] = *reinterpret_cast<int (*)[4]>(&A.ia[4]);
+    int (&bA)[4] = *reinterpret_cast<int (*)[4]>(&A.ib[0]);
+    int (&bB)[4] = *reinterpret_cast<int (*)[4]>(&A.ib[4]);
+    // A rows g / g+8 = columns (c0, c1) resp. (c2, c3); logical k 4t+i <-> nibble 2i, 16+4t+i <-> nibble 2i+1 of k8-row t
+    imma_u8s8(aA, lo0, lo1, hi0, hi1, xb.x, xb.y);
+    imma_u8u8(bA, lo0, lo1, hi0, hi1, xb.z, xb.w);
+    imma_u8s8(aB, lo2, lo3, hi2, hi3, xb.x, xb.y);
+    imma_u8u8(bB, lo2, lo3, hi2, hi3, xb.z, xb.w);
 }
 
 __device__ __forceinline__ void mbar_arrive(void* bar)
@@ -265,8 +298,8 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
     unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);    // NST x STAGE_BYTES, 1 KB aligned (swizzle atom)
     unsigned char* sc_s = ring + NST * STAGE_BYTES;                               // GMAXC x 256
     unsigned char* zq_s = sc_s + GMAXC * SC_ROW;                                  // GMAXC x 64 (raw packed zeros)
-    unsigned char* zs_s = zq_s + GMAXC * ZQ_ROW;                                  // GMAXC x 512 (half2(1024 + zp) per column)
-    float* red = reinterpret_cast<float*>(zs_s + GMAXC * ZS_ROW);                 // WK x 8 x RED_LD
+    unsigned char* seg_s = zq_s + GMAXC * ZQ_ROW;                                 // GMAXC x 8 tokens x {sum x_q, x scale}
+    float* red = reinterpret_cast<float*>(seg_s + SEG_BYTES);                     // WK x 8 x RED_LD
     float* slots = red + WK * GV_MAXM * RED_LD;                                   // 2 x cs x M x 128 (cluster reduction)
     unsigned char* xs = reinterpret_cast<unsigned char*>(slots + 2 * cs * M * GV_TILE_N);   // M x xs_stride
     __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST], sc_bar;
@@ -362,9 +395,10 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
 
         Accum A;
         #pragma unroll
-        for (int j = 0; j < 8; j++) { A.acc[j] = 0.f; A.cg[j] = 0.f; }
+        for (int j = 0; j < 8; j++) { A.acc[j] = 0.f; A.ia[j] = 0; A.ib[j] = 0; }
         #pragma unroll
-        for (int j = 0; j < 4; j++) { A.cs[j] = 0.f; A.zs[j] = 0; A.zf[j] = 0; }
+        for (int j = 0; j < 4; j++) A.cs[j] = 0.f;
+        A.zp4 = 0; A.sxq[0] = A.sxq[1] = 0; A.sxs[0] = A.sxs[1] = 0.f;
         A.cur_grp = -1;
 
         for (int c0 = sg0; c0 < sg1; c0 += a.chunk_stages) {
@@ -413,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                 }
             }
 
-            // ---- stage x[:, c0*128 .. c1*128) into smem, permuted (0,4,1,5,2,6,3,7) inside each 8-block ----
+            // ---- stage x[:, c0*128 .. c1*128) into smem (pass 1: fp16 after the act-order gather / RMS norm) ----
             {
                 const int nk8 = (c1 - c0) * STAGE_ROWS;
                 const int k8_0 = c0 * STAGE_ROWS;
@@ -452,28 +486,74 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                             }
                         }
                     }
-                    uint4 o;
-                    o.x = __byte_perm(xv.x, xv.z, 0x5410);   // {h0, h4}
-                    o.y = __byte_perm(xv.x, xv.z, 0x7632);   // {h1, h5}
-                    o.z = __byte_perm(xv.y, xv.w, 0x5410);   // {h2, h6}
-                    o.w = __byte_perm(xv.y, xv.w, 0x7632);   // {h3, h7}
-                    *reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)j * 16) = o;
+                    *reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)j * 16) = xv;   // fp16, natural order (pass 1)
+                }
+            }
+            consumer_sync();
+            // ---- pass 2: quantise each (token, segment) of the staged x to 16-bit integers with its own scale, in place ----
+            {
+                const int nseg = g_hi - g_lo + 1;
+                const int rows_lo = c0 * STAGE_ROWS, rows_hi = min(c1 * STAGE_ROWS, k8_lim);
+                const int nrows = (c1 - c0) * STAGE_ROWS;
+                const int rpg = a.groups > 1 ? (4 << a.gs_shift32) : (1 << 30);       // k8-rows per quantisation group
+                uint4* table = reinterpret_cast<uint4*>(seg_s);
+                for (int idx = tid; idx < nseg * (GV_MAXM - M); idx += CONSUMERS)       // unused tokens: scale 0
+                    table[(idx / (GV_MAXM - M)) * GV_MAXM + M + idx % (GV_MAXM - M)] = make_uint4(0, 0, 0, 0);
+                if (rpg <= STAGE_ROWS) {
+                    // a segment is rpg (4, 8 or 16) consecutive rows inside one ring stage: one thread per row,
+                    // max / sum over the segment with width-rpg shuffles (nrows and the thread count are multiples of rpg)
+                    for (int base = 0; base < M * nrows; base += CONSUMERS) {
+                        const int idx = base + tid;
+                        const bool act = idx < M * nrows;
+                        const int m = act ? idx / nrows : 0, rr = act ? idx - m * nrows : 0;
+                        uint4* rp = reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)rr * 16);
+                        const uint4 hv = act ? *rp : make_uint4(0, 0, 0, 0);
+                        float mx = row_absmax(hv);
+                        for (int o = rpg >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        uint4 q;
+                        int sum = quantise_row(hv, mx > 0.f ? 32767.0f / mx : 0.f, q);
+                        for (int o = rpg >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                        if (act) {
+                            *rp = q;
+                            const int r = rows_lo + rr;                       // absolute k8-row
+                            if ((r & (rpg - 1)) == 0) {
+                                const int gi = r / rpg - g_lo;
+                                const int par = (jbase + (r / STAGE_ROWS - sg0)) & 1;   // k-warp that consumes this ring stage
+                                table[gi * GV_MAXM + m] = make_uint4(par ? 0u : (uint32_t)sum, par ? (uint32_t)sum : 0u,
+                                                                     __float_as_uint(mx * (1.0f / 32767.0f)), 0u);
+                            }
+                        }
+                    }
+                } else {
+                    // large groups (groupsize >= 256 or a single group): one warp per (segment, token)
+                    for (int task = warp; task < nseg * M; task += CONSUMERS / 32) {
+                        const int gi = task / M, m = task - gi * M;
+                        int r_lo = rows_lo, r_hi = rows_hi;
+                        if (a.groups > 1) { r_lo = max(rows_lo, (g_lo + gi) * rpg); r_hi = min(rows_hi, (g_lo + gi + 1) * rpg); }
+                        unsigned char* xrow_p = xs + (size_t)m * a.xs_stride;
+                        float mx = 0.f;
+                        for (int r = r_lo + lane; r < r_hi; r += 32)
+                            mx = fmaxf(mx, row_absmax(*reinterpret_cast<const uint4*>(xrow_p + (size_t)(r - rows_lo) * 16)));
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        const float inv = mx > 0.f ? 32767.0f / mx : 0.f;
+                        int sum0 = 0, sum1 = 0;
+                        for (int r = r_lo + lane; r < r_hi; r += 32) {
+                            uint4* rp = reinterpret_cast<uint4*>(xrow_p + (size_t)(r - rows_lo) * 16);
+                            uint4 q;
+                            const int sm = quantise_row(*rp, inv, q);
+                            *rp = q;
+                            if ((jbase + (r / STAGE_ROWS - sg0)) & 1) sum1 += sm; else sum0 += sm;
+                        }
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) { sum0 += __shfl_xor_sync(0xffffffffu, sum0, o); sum1 += __shfl_xor_sync(0xffffffffu, sum1, o); }
+                        if (lane == 0) table[gi * GV_MAXM + m] = make_uint4((uint32_t)sum0, (uint32_t)sum1, __float_as_uint(mx * (1.0f / 32767.0f)), 0u);
+                    }
                 }
             }
             mbar_wait(&sc_bar, sc_parity);   // scales / zeros landed
             sc_parity ^= 1;
-            // expand the packed zeros into the per-column constants the unpack uses: half2(1024 + (z + 1))
-            for (int idx = tid; idx < (g_hi - g_lo + 1) * (GV_TILE_N / 8); idx += CONSUMERS) {
-                const int gi = idx >> 4, wd = idx & 15;
-                const uint32_t zw = *reinterpret_cast<const uint32_t*>(zq_s + gi * ZQ_ROW + wd * 4);
-                uint32_t o[8];
-                #pragma unroll
-                for (int j = 0; j < 8; j++) o[j] = (0x6401u + ((zw >> (4 * j)) & 0xfu)) * 0x00010001u;
-                uint4* dst = reinterpret_cast<uint4*>(zs_s + gi * ZS_ROW + wd * 32);
-                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            }
-            consumer_sync();                 // x and zero constants staged
+            consumer_sync();                 // quantised x, segment table, scales and zeros are in place
 
             // Whole stages alternate between the two k-warps (stage j of this CTA goes to k-warp j & 1), so a warp
             // sees 128 consecutive k per stage and switches quantisation group at most once per 4 units (gs >= 128).
@@ -482,7 +562,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
             const uint32_t wa_odd = smem_u32(ring) + wn * BOX_BYTES + (t + 4) * 128 + ((pg ^ (t + 4)) << 4); // rows t+4, t+12
             const uint32_t xa0 = smem_u32(xs) + (uint32_t)xrow * (uint32_t)a.xs_stride + (uint32_t)t * 16u;
             const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-            const uint32_t sc_a = smem_u32(sc_s), zs_a = smem_u32(zs_s);
+            const uint32_t sc_a = smem_u32(sc_s), zq_a = smem_u32(zq_s), seg_a = smem_u32(seg_s);
             const bool tail_checks = (K % STAGE_K) != 0;       // only a ragged last stage needs per-unit bounds checks
             const bool skip_math = !col_ok || (a.debug & 5);
             // first stage of this chunk that belongs to this k-warp: global stage counter parity == wk
@@ -502,8 +582,8 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                     #define GV_UNIT(U_, W_, X_)                                                            \
                         if (!tail_checks || ((u0 + U_) * 4 + 4) <= k8_lim) {                               \
                             const int grp = (u0 + U_) >> a.gs_shift32;                                     \
-                            if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zs_a, lane_col);        \
-                            unit_mma(A, W_, X_, a.debug);                                                  \
+                            if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zq_a, seg_a, lane_col, t, wk); \
+                            unit_mma(A, W_, X_);                                                           \
                         }
                     GV_UNIT(0, w0, x0) GV_UNIT(1, w1, x1) GV_UNIT(2, w2, x2) GV_UNIT(3, w3, x3)
                     #undef GV_UNIT
@@ -511,13 +591,10 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(empty0 + slot * 8);
             }
+            // x scales are per (segment, chunk): close the open segment before the staging buffers are recycled
+            if (A.cur_grp >= 0) { seg_flush(A); A.cur_grp = -1; }
         }
         jbase += sg1 - sg0;
-        if (A.cur_grp >= 0) {
-            #pragma unroll
-            for (int j = 0; j < 8; j++) A.acc[j] = fmaf(A.cs[j >> 1], A.cg[j], A.acc[j]);
-        }
-
         // ---- reduce the WK k-warps through shared memory: red[wk][m][col] ----
         {
             float* r = red + (size_t)wk * GV_MAXM * RED_LD;
@@ -630,14 +707,40 @@ int launch_cfg(ExlDevice* ds, GemvArgs& a, int items, cudaStream_t stream)
         EXL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_device_done[ds->device] = 1;
     }
-    // K split factor == cluster size: as large as keeps every CTA of the launch co-resident (2 CTAs / SM)
-    const int cap = ds->num_sms * 2;
-    int cs = MAX_CS;
-    while (cs > 1 && ((long long)items * cs > cap || cs > a.spt || 2 * cs * a.M * GV_TILE_N * (int)sizeof(float) > SLOT_BUDGET)) cs >>= 1;
+    // K split factor == cluster size: the largest (<= 8) that keeps every cluster of the launch co-resident.
+    static int cap_mult = -1;
+    if (cap_mult < 0) { const char* e = getenv("EXL_GV_CAP"); cap_mult = e ? atoi(e) : 2; }
+    const int cap = ds->num_sms * cap_mult;
+    auto smem_for = [&](int c) {
+        return (size_t)1024 + (size_t)NST * STAGE_BYTES + (size_t)GMAXC * (SC_ROW + ZQ_ROW) + SEG_BYTES +
+               (size_t)WK * GV_MAXM * RED_LD * sizeof(float) + (size_t)2 * c * a.M * GV_TILE_N * sizeof(float) + (size_t)a.M * a.xs_stride;
+    };
+    // max co-resident clusters per cluster size, measured once per (device, M) with the occupancy API
+    static int max_clusters[EXL_MAX_DEVICES][GV_MAXM + 1][MAX_CS + 1] = {};
+    auto clusters_fit = [&](int c) -> int {
+        int& cached = max_clusters[ds->device][a.M][c];
+        if (cached == 0) {
+            cudaLaunchConfig_t q; memset(&q, 0, sizeof(q));
+            q.gridDim = dim3((unsigned)(c * 64)); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = smem_for(c);
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int n = 0;
+            if (c == 1 || cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = cap / c; }
+            cached = n > 0 ? n : -1;
+        }
+        return cached;
+    };
+    int cs = 1;
+    for (int c = MAX_CS; c > 1; c--) {
+        if ((long long)items * c > cap || c > a.spt) continue;
+        if (2 * c * a.M * GV_TILE_N * (int)sizeof(float) > SLOT_BUDGET) continue;
+        if (clusters_fit(c) < items) continue;
+        cs = c; break;
+    }
     if (force_cs >= 1 && force_cs <= MAX_CS && force_cs <= a.spt && 2 * force_cs * a.M * GV_TILE_N * (int)sizeof(float) <= SLOT_BUDGET) cs = force_cs;
     a.cs = cs;
-    const size_t smem = 1024 + (size_t)NST * STAGE_BYTES + (size_t)GMAXC * (SC_ROW + ZQ_ROW + ZS_ROW) + (size_t)WK * GV_MAXM * RED_LD * sizeof(float) +
-                        (size_t)2 * cs * a.M * GV_TILE_N * sizeof(float) + (size_t)a.M * a.xs_stride;
+    const size_t smem = smem_for(cs);
 
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
