@@ -229,10 +229,11 @@ static int q4_matmul_dispatch(ExlDevice* ds, const half* x, int M, const exl_q4_
     if (M <= 0) return EXL_OK;
     int path = force_path;
     if (path == 0) {
+        // M <= 8: one skinny pass.  8 < M <= 48: still HBM-bound, a few skinny passes (each re-streams the packed weights,
+        // 0.5 B / weight) beat a tensor-core tile that is mostly padding.  Above: tcgen05 fused-dequant GEMM.
         if (M <= EXL_SKINNY_MAX_M) path = 1;
-        else if (exl_tc_gemm_supported(w, M)) path = 2;
-        else if (M <= 64) path = 1;            // HBM-bound regime: a few skinny passes beat dequant-to-HBM + GEMM
-        else path = 3;
+        else if (M <= 48 || !exl_tc_gemm_supported(w, M)) path = (M <= 64) ? 1 : 3;
+        else path = 2;
     }
     if (path == 1) {
         g_last_q4_path = "skinny_mma";

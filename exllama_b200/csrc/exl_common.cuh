@@ -25,6 +25,8 @@ struct exl_q4_matrix
     uint32_t* x_map;     // [K] or nullptr (act-order: x column feeding sequential row k)
     // TMA descriptor of qweight as a 2-D int32 tensor [K/8, N], box 16 rows x 32 columns, 128-byte swizzle (q4_gemv.cu)
     alignas(64) CUtensorMap tmap_w;
+    // same tensor, box 8 rows x 128 columns, no swizzle: the packed-word tile of one k-block of the tcgen05 GEMM (q4_gemm_tc.cu)
+    alignas(64) CUtensorMap tmap_wp;
 };
 
 struct ExlTuning

@@ -78,6 +78,11 @@ int exl_encode_weight_tmap(exl_q4_matrix* w)
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for K=%d N=%d", (int)r, w->K, w->N);
+    const cuuint32_t box_p[2] = {128, 8};                              // 128 columns x 8 k8-rows (one 64-wide k-block), dense
+    r = encode(&w->tmap_wp, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)w->qweight, dims, strides, box_p, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled (prefill box) failed (%d) for K=%d N=%d", (int)r, w->K, w->N);
     return EXL_OK;
 }
 

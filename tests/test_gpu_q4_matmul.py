@@ -134,6 +134,31 @@ def test_recons_cublas_path(oracle, M, K, N, gs, act):
     assert_close_ref64(out.cpu().numpy(), ref, what="recons")
 
 
+TC_CASES = [(128, 1024, 512, 128, False), (200, 2048, 384, 32, True), (1, 512, 128, 64, False), (77, 4096, 1152, 128, True),
+            (384, 1024, 1024, 1024, False), (130, 2816, 96, 128, False)]
+
+
+@pytest.mark.parametrize("M,K,N,gs,act", TC_CASES)
+def test_tcgen05_gemm_vs_ref64(oracle, M, K, N, gs, act):
+    """force_path=2: the tcgen05 fused-dequant GEMM.  Its B operand is bit-identical to the reference's reconstructed
+    weights (fp16-rounded scale * (q - zp)), accumulated in fp32 -> compare against the `recons` flavour of ref64."""
+    import torch
+    from exllama_b200 import capi
+    qw, qz, sc, g_idx = _mk(oracle, K, N, gs, act, seed=K + N + M)
+    x = oracle.synth_x(M, K, seed=M)
+    q4 = _q4(capi, qw, qz, sc, g_idx)
+    out = capi.q4_matmul(to_cuda(x), q4, force_path=2)
+    torch.cuda.synchronize()
+    assert capi.last_q4_path() == "tc_gemm"
+    ref = oracle.ref64_with_act_order(x, qw, qz, sc, g_idx, recons=True)
+    assert_close_ref64(out.cpu().numpy(), ref, what=f"tc_gemm M{M} K{K} N{N} g{gs} act{act}")
+    res = oracle.synth_x(M, N, seed=99)
+    out2 = to_cuda(res.copy())
+    capi.q4_matmul(to_cuda(x), q4, out=out2, no_zero=True, force_path=2)
+    ref2 = oracle.ref64_with_act_order(x, qw, qz, sc, g_idx, acc_in=res, recons=True)
+    assert_close_ref64(out2.cpu().numpy(), ref2, what="tc_gemm accumulate")
+
+
 def test_reconstruct_bit_exact(oracle):
     from exllama_b200 import capi
     for (K, N, gs) in [(256, 64, 32), (1024, 384, 128)]:
