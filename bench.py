@@ -206,7 +206,8 @@ def main():
     torch.cuda.synchronize()
 
     graph = None
-    if not args.no_graph:
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("EXL_BENCH_TP_GRAPH", "0") == "1")
+    if use_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -214,7 +215,7 @@ def main():
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             glogits = step_eager()
 
     def step_device():
@@ -228,11 +229,13 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.cudart().cudaProfilerStart()          # no-op unless run under `ncu --profile-from-start off`
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     clocks = sampler.result()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)

@@ -39,6 +39,8 @@ SIGNATURES = {
                     [vp, vp, i32] * 3 + [vp, i32, vp]),
     "exl_q4_attn_2": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     "exl_q4_mlp": (i32, [vp, vp, f32, vp, vp, vp, i32, i32] + [vp, vp, i32] * 3 + [vp, i32, vp]),
+    "exl_q4_attn_2_tp": (i32, [vp, vp, vp, i32, i32, vp]),
+    "exl_q4_mlp_tp": (i32, [vp, vp, f32, vp, vp, vp, i32, i32, i32, i32, vp]),
     "exl_rep_penalty": (i32, [i32, vp, vp, f32, i32, i32, i32]),
     "exl_apply_rep_penalty": (i32, [i32, vp, f32, i32, i32, i32, vp]),
     "exl_q4_matmul_host": (i32, [vp, i32, vp, vp, vp, vp, vp]),

@@ -411,10 +411,10 @@ int exl_q4_attn_2(void* x, const void* attn_output, const exl_q4_matrix* o_proj,
     return q4_matmul_dispatch(ds, (const half*)attn_output, height, o_proj, (half*)x, true, 0, stream);
 }
 
-int exl_q4_mlp(void* x_, const void* rms_norm_weight, float epsilon, const exl_q4_matrix* gate, const exl_q4_matrix* up,
+static int q4_mlp_impl(void* x_, const void* rms_norm_weight, float epsilon, const exl_q4_matrix* gate, const exl_q4_matrix* up,
                const exl_q4_matrix* down, int height, int dim, const void* gate_a, const void* gate_b, int gate_rank,
                const void* up_a, const void* up_b, int up_rank, const void* down_a, const void* down_b, int down_rank,
-               void* lora_temp, int device, void* stream_)
+               void* lora_temp, int device, void* stream_, bool add_residual)
 {
     if (!gate || !up || !down) return exl_set_err(EXL_ERR_STATE, "q4_mlp: NULL handle");
     ExlDevice* ds = exl_device_state(device);
@@ -442,7 +442,7 @@ int exl_q4_mlp(void* x_, const void* rms_norm_weight, float epsilon, const exl_q
         GemvFused f; f.norm_w = (const half*)rms_norm_weight; f.eps = epsilon;
         int rc = exl_gemv_launch(ds, x, height, mats, outs, 2, false, GV_PRO_RMSNORM, GV_EPI_SILU_MUL, &f, stream);
         if (rc != EXL_OK) return rc;
-        return q4_matmul_dispatch(ds, temp_mlp, height, down, x, true, 0, stream);
+        return q4_matmul_dispatch(ds, temp_mlp, height, down, x, add_residual, 0, stream);
     }
 
     half* temp_x = have_norm ? ds->temp_state + (size_t)height * dim : own;
@@ -464,7 +464,32 @@ int exl_q4_mlp(void* x_, const void* rms_norm_weight, float epsilon, const exl_q
         rc = exl_half_matmul_cublas_launch(ds, t0, (const half*)down_a, (half*)lora_temp, height, inter, down_rank, false, stream); if (rc) return rc;
         rc = exl_half_matmul_cublas_launch(ds, (const half*)lora_temp, (const half*)down_b, x, height, down_rank, dim, true, stream); if (rc) return rc;
     }
-    return q4_matmul_dispatch(ds, t0, height, down, x, true, 0, stream);
+    return q4_matmul_dispatch(ds, t0, height, down, x, add_residual || down_rank != 0, 0, stream);
+}
+
+int exl_q4_mlp(void* x_, const void* rms_norm_weight, float epsilon, const exl_q4_matrix* gate, const exl_q4_matrix* up,
+               const exl_q4_matrix* down, int height, int dim, const void* gate_a, const void* gate_b, int gate_rank,
+               const void* up_a, const void* up_b, int up_rank, const void* down_a, const void* down_b, int down_rank,
+               void* lora_temp, int device, void* stream_)
+{
+    return q4_mlp_impl(x_, rms_norm_weight, epsilon, gate, up, down, height, dim, gate_a, gate_b, gate_rank, up_a, up_b, up_rank,
+                       down_a, down_b, down_rank, lora_temp, device, stream_, true);
+}
+
+int exl_q4_mlp_tp(void* x, const void* rms_norm_weight, float epsilon, const exl_q4_matrix* gate, const exl_q4_matrix* up,
+                  const exl_q4_matrix* down, int height, int dim, int add_residual, int device, void* stream)
+{
+    return q4_mlp_impl(x, rms_norm_weight, epsilon, gate, up, down, height, dim, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                       nullptr, nullptr, 0, nullptr, device, stream, add_residual != 0);
+}
+
+int exl_q4_attn_2_tp(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, int add_residual, void* stream)
+{
+    if (!o_proj) return exl_set_err(EXL_ERR_STATE, "q4_attn_2_tp: NULL handle");
+    ExlDevice* ds = exl_device_state(o_proj->device);
+    if (!ds) return EXL_ERR_CUDA;
+    DeviceGuard guard(o_proj->device);
+    return q4_matmul_dispatch(ds, (const half*)attn_output, height, o_proj, (half*)x, add_residual != 0, 0, (cudaStream_t)stream);
 }
 
 int exl_q4_matmul_host(const void* x_host, int M, const exl_q4_matrix* w, void* out_host, void* d_x, void* d_out, void* stream_)

@@ -231,6 +231,27 @@ void apply_rep_penalty(torch::Tensor sequence, float penalty_max, int sustain, i
                                        sustain, decay, seq_len, ((float*)logits.data_ptr()) + (size_t)i * vocab_size));
 }
 
+// ---- tensor-parallel additions (not part of the reference surface) -------------------------------------------------
+void q4_attn_2_tp(torch::Tensor x, torch::Tensor attn_output, uintptr_t o_proj, bool add_residual)
+{
+    CHECK_DTYPE(x, kHalf);
+    CHECK_DTYPE(attn_output, kHalf);
+    const at::cuda::OptionalCUDAGuard device_guard(x.device());
+    EXL_CALL(exl_q4_attn_2_tp(x.data_ptr(), attn_output.data_ptr(), H(o_proj), (int)x.size(0), add_residual, cur_stream()));
+}
+
+void q4_mlp_tp(torch::Tensor x, torch::Tensor rms_norm_weight, float epsilon, uintptr_t gate, uintptr_t up, uintptr_t down, bool add_residual)
+{
+    CHECK_DTYPE(x, kHalf);
+    CHECK_DTYPE(rms_norm_weight, kHalf);
+    torch::Device device = x.device();
+    const int device_index = device.index();
+    CHECK_DEVICE_INDEX(device_index);
+    const at::cuda::OptionalCUDAGuard device_guard(device);
+    EXL_CALL(exl_q4_mlp_tp(x.data_ptr(), rms_norm_weight.data_ptr(), epsilon, H(gate), H(up), H(down), (int)x.size(0), (int)x.size(1),
+                           add_residual, device_index, cur_stream()));
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
     m.def("set_tuning_params", &set_tuning_params, "set_tuning_params");
@@ -249,4 +270,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("half_matmul_cublas", &half_matmul_cublas, "half_matmul_cublas");
     m.def("rep_penalty", &rep_penalty, "rep_penalty");
     m.def("apply_rep_penalty", &apply_rep_penalty, "apply_rep_penalty");
+    // additions for tensor parallelism
+    m.def("q4_attn_2_tp", &q4_attn_2_tp, "q4_attn_2_tp");
+    m.def("q4_mlp_tp", &q4_mlp_tp, "q4_mlp_tp");
 }

@@ -72,22 +72,12 @@ def row_parallel_residual(ext, x, inp, q4, rank, group):
     """x (replicated, [M, hidden]) += all_reduce(inp_local . W_rowshard).
     Rank 0 folds the residual into its partial (no_zero accumulate, exactly q4_attn_2); the other ranks
     overwrite their copy of x with their partial, so one in-place all-reduce leaves x_old + sum(partials) everywhere."""
-    import torch
-    from . import cuda_ext
-    none = cuda_ext.none_tensor
-    if rank == 0:
-        ext.q4_attn_2(x, inp, q4, none, none, none)
-    else:
-        ext.q4_matmul(inp, q4, x)
+    ext.q4_attn_2_tp(x, inp, q4, rank == 0)
     all_reduce(x, group)
 
 
 def mlp_tp(ext, cuda_ext, x, L, eps, rank, group):
-    """Tensor-parallel MLP block: local [norm -> gate,up -> silu*mul] then row-parallel down + all-reduce."""
-    import torch
-    none = cuda_ext.none_tensor
-    xn = cuda_ext.ext_rms_norm(x, L.ln2, eps)
-    g = cuda_ext.ext_q4_matmul(xn, L.gate.q4, L.gate.width)
-    u = cuda_ext.ext_q4_matmul(xn, L.up.q4, L.up.width)
-    act = torch.nn.functional.silu(g) * u
-    row_parallel_residual(ext, x, act, L.down.q4, rank, group)
+    """Tensor-parallel MLP block: the same two fused launches as the single-GPU q4_mlp ([norm -> gate,up -> silu*mul],
+    [down]) on this rank's column / row shards, then ONE all-reduce of the [M, hidden] partial."""
+    ext.q4_mlp_tp(x, L.ln2, eps, L.gate.q4, L.up.q4, L.down.q4, rank == 0)
+    all_reduce(x, group)

@@ -148,6 +148,16 @@ int exl_q4_mlp(void* x, const void* rms_norm_weight, float epsilon,
                const void* down_a, const void* down_b, int down_rank,
                void* lora_temp, int device, void* stream);
 
+/* --- tensor-parallel variants (new functionality; the reference has no tensor parallelism) ----- */
+
+/* As exl_q4_attn_2 / exl_q4_mlp, but with add_residual == 0 the row-parallel projection OVERWRITES x with this rank's
+   partial product instead of accumulating into it, so that one in-place all-reduce over the ranks (rank 0 keeps the
+   residual) yields x_old + sum(partials) everywhere. */
+int exl_q4_attn_2_tp(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, int add_residual, void* stream);
+int exl_q4_mlp_tp(void* x, const void* rms_norm_weight, float epsilon,
+                  const exl_q4_matrix* gate, const exl_q4_matrix* up, const exl_q4_matrix* down,
+                  int height, int dim, int add_residual, int device, void* stream);
+
 /* --- sampling helper (CPU, like the reference) --------------------------------- */
 
 /* cpu_func/rep_penalty.cpp:5-31 */

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the tensor-parallel path (run under torchrun, one rank per GPU, NCCL):
+identical full GPTQ tensors on every rank -> column / row shards -> q4_attn_2_tp / q4_mlp_tp + one all-reduce each;
+rank 0 compares with the single-rank float64 oracle.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/tp_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from exllama_b200 import cuda_ext, tp  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{os.environ['LOCAL_RANK']}"))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+ext = cuda_ext.exllama_ext
+hidden, inter, heads, gs = 1024, 2816 if world <= 2 else 5632, 8, 128
+plan = tp.plan_shards(hidden, inter, heads, hidden // heads, gs, world)
+full = {n: O.synth_q4(K, N, gs, seed=s)[:3] for n, K, N, s in [("o", hidden, hidden, 10), ("gate", hidden, inter, 11), ("up", hidden, inter, 12), ("down", inter, hidden, 13)]}
+x = O.synth_x(3, hidden, seed=14); attn = O.synth_x(3, hidden, seed=15)
+w = (1 + 0.1 * np.random.default_rng(0).standard_normal(hidden)).astype(np.float16)
+c0, c1 = plan.head_cols[rank]; i0, i1 = plan.inter_cols[rank]
+
+
+def mk(t):
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in t]
+    return cuda_ext.ext_make_q4(t[0], t[1], t[2], None, dev.index), t
+
+
+o_q4, k1 = mk(tp.shard_q4_rows(*full["o"], c0, c1, gs))
+g_q4, k2 = mk(tp.shard_q4_columns(*full["gate"], i0, i1))
+u_q4, k3 = mk(tp.shard_q4_columns(*full["up"], i0, i1))
+d_q4, k4 = mk(tp.shard_q4_rows(*full["down"], i0, i1, gs))
+
+
+class L: pass
+
+
+layer = L(); layer.ln2 = torch.from_numpy(w).to(dev)
+layer.gate = L(); layer.gate.q4 = g_q4; layer.up = L(); layer.up.q4 = u_q4; layer.down = L(); layer.down.q4 = d_q4
+tx = torch.from_numpy(x.copy()).to(dev)
+tp.row_parallel_residual(ext, tx, torch.from_numpy(np.ascontiguousarray(attn[:, c0:c1])).to(dev), o_q4, rank, None)
+x1 = tx.cpu().numpy()
+tp.mlp_tp(ext, cuda_ext, tx, layer, 1e-6, rank, None)
+x2 = tx.cpu().numpy()
+torch.cuda.synchronize()
+if rank == 0:
+    r1 = O.q4_matmul_f64(attn, *full["o"], acc_in=x)
+    e1 = np.abs(x1.astype(np.float64) - r1).max() / np.sqrt(np.mean(r1 ** 2))
+    xn, _ = O.rms_norm(x1, w, 1e-6)
+    g = O.q4_matmul_f64(xn, *full["gate"]).astype(np.float16); u = O.q4_matmul_f64(xn, *full["up"]).astype(np.float16)
+    r2 = O.q4_matmul_f64(O.silu_mul(g, u), *full["down"], acc_in=x1)
+    e2 = np.abs(x2.astype(np.float64) - r2).max() / np.sqrt(np.mean(r2 ** 2))
+    ok = e1 < 5e-3 and e2 < 1e-2
+    print(f"tp_check world={world}: attn_2 max err/rms {e1:.2e}, mlp max err/rms {e2:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    if not ok:
+        sys.exit(1)
+dist.barrier()
+dist.destroy_process_group()
