@@ -290,12 +290,21 @@ def main():
     ext = cuda_ext.exllama_ext
     kern_rows = []
 
-    def time_launches(fn, reps=5):
+    def time_launches(fn, reps=8):
+        """mean device time of one pass of fn, replayed as a CUDA graph (no host overhead inside the timed region)"""
         fn(); torch.cuda.synchronize()
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
-            fn()
+            g.replay()
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e3 / reps       # us per pass
 
@@ -323,8 +332,12 @@ def main():
                          ("down (+residual)", us_down, b_down), ("o_proj (+residual)", us_o, b_o)):
         kern_rows.append({"kernel": name, "us": round(us, 3), "bytes": by, "GBps": round(by / us / 1e3, 1), "frac": round(by / us / 1e3 / hbm_peak, 4)})
     dom = kern_rows[0]
+    traffic = None
+    tp_path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if world == 1 and args.model == "7b" and gs == 128 and os.path.exists(tp_path):
+        traffic = json.load(open(tp_path)).get("traffic")      # dram read+write of this kernel from the committed ncu --set full capture
     roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "kernel": "q4_gemv_kernel<RMSNORM,SILU_MUL> (fused gate+up)", "peak_kind": peak_kind,
+                "traffic": traffic, "kernel": "q4_gemv_kernel<RMSNORM,SILU_MUL> (fused gate+up)", "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]}
 
     # ------------------------------------------------------------------ prefill

@@ -54,7 +54,7 @@ constexpr int SC_ROW = GV_TILE_N * 2;      // bytes of scales per group row in s
 constexpr int ZQ_ROW = GV_TILE_N / 2;      // bytes of packed zeros per group row in smem (raw, as TMA delivers them)
 constexpr int SEG_BYTES = GMAXC * GV_MAXM * 16;  // per (segment, token): {sum of x_q over even ring stages, over odd ring stages, x scale, -}
 constexpr int XS_BUDGET = 16 * 1024;       // bytes of staged x per chunk
-constexpr int SLOT_BUDGET = 8 * 1024;      // bytes of cluster-reduction slots (2 x CS x M x 512 B)
+constexpr int SLOT_BUDGET = 16 * 1024;     // bytes of cluster-reduction slots (2 x CS x M x 512 B)
 constexpr int MAX_CS = 8;
 
 struct GemvMatDev
@@ -150,6 +150,18 @@ __device__ __forceinline__ void imma_u8u8(int (&c)[4], uint32_t a0, uint32_t a1,
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// first MMA of a segment: C = 0 (no separate clearing of the 16 integer accumulators)
+__device__ __forceinline__ void imma_u8s8_z(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+__device__ __forceinline__ void imma_u8u8_z(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
 __device__ __forceinline__ half silu_h(half x)
 {
     // same fp16 sequence as the reference (q4_mlp.cu:27-36)
@@ -174,6 +186,7 @@ struct Accum
     int sxq[2];          // per token (2t, 2t+1): sum of x_q over the part of the segment this k-warp accumulates
     float sxs[2];        // per token: x scale of the segment
     int cur_grp;
+    bool fresh;          // integer accumulators are logically zero: the next MMA starts from C = 0
 };
 
 __device__ __forceinline__ void seg_flush(Accum& A)
@@ -184,12 +197,12 @@ __device__ __forceinline__ void seg_flush(Accum& A)
         const int zp = (int)((A.zp4 >> (8 * col)) & 0xffu);
         const int val = A.ia[j] * 256 + A.ib[j] - zp * A.sxq[tok];
         A.acc[j] = fmaf(A.cs[col] * A.sxs[tok], (float)val, A.acc[j]);
-        A.ia[j] = 0; A.ib[j] = 0;
     }
+    A.fresh = true;
 }
 
 __device__ __forceinline__ void group_switch(Accum& A, int grp, int g_lo, uint32_t sc_addr, uint32_t zq_addr, uint32_t seg_addr,
-                                             int lane_col, int t, int wk)
+                                             int lane_col, int t, int par)
 {
     if (A.cur_grp >= 0) seg_flush(A);
     const int gl = grp - g_lo;
@@ -205,8 +218,8 @@ __device__ __forceinline__ void group_switch(Accum& A, int grp, int g_lo, uint32
     A.cs[2] = __low2float(s23); A.cs[3] = __high2float(s23);
     const uint32_t z4 = zw >> ((lane_col & 4) * 4);          // this lane's 4 zero nibbles
     A.zp4 = ((z4 & 0xfu) | ((z4 & 0xf0u) << 4) | ((z4 & 0xf00u) << 8) | ((z4 & 0xf000u) << 12)) + 0x01010101u;
-    A.sxq[0] = (int)(wk ? s0.y : s0.x); A.sxs[0] = __uint_as_float(s0.z);
-    A.sxq[1] = (int)(wk ? s1.y : s1.x); A.sxs[1] = __uint_as_float(s1.z);
+    A.sxq[0] = (int)(par ? s0.y : s0.x); A.sxs[0] = __uint_as_float(s0.z);
+    A.sxq[1] = (int)(par ? s1.y : s1.x); A.sxs[1] = __uint_as_float(s1.z);
     A.cur_grp = grp;
 }
 
@@ -251,10 +264,18 @@ __device__ __forceinline__ void unit_mma(Accum& A, const uint4& w, const uint4& 
     int (&bA)[4] = *reinterpret_cast<int (*)[4]>(&A.ib[0]);
     int (&bB)[4] = *reinterpret_cast<int (*)[4]>(&A.ib[4]);
     // A rows g / g+8 = columns (c0, c1) resp. (c2, c3); logical k 4t+i <-> nibble 2i, 16+4t+i <-> nibble 2i+1 of k8-row t
-    imma_u8s8(aA, lo0, lo1, hi0, hi1, xb.x, xb.y);
-    imma_u8u8(bA, lo0, lo1, hi0, hi1, xb.z, xb.w);
-    imma_u8s8(aB, lo2, lo3, hi2, hi3, xb.x, xb.y);
-    imma_u8u8(bB, lo2, lo3, hi2, hi3, xb.z, xb.w);
+    if (A.fresh) {                 // warp-uniform
+        imma_u8s8_z(aA, lo0, lo1, hi0, hi1, xb.x, xb.y);
+        imma_u8u8_z(bA, lo0, lo1, hi0, hi1, xb.z, xb.w);
+        imma_u8s8_z(aB, lo2, lo3, hi2, hi3, xb.x, xb.y);
+        imma_u8u8_z(bB, lo2, lo3, hi2, hi3, xb.z, xb.w);
+        A.fresh = false;
+    } else {
+        imma_u8s8(aA, lo0, lo1, hi0, hi1, xb.x, xb.y);
+        imma_u8u8(bA, lo0, lo1, hi0, hi1, xb.z, xb.w);
+        imma_u8s8(aB, lo2, lo3, hi2, hi3, xb.x, xb.y);
+        imma_u8u8(bB, lo2, lo3, hi2, hi3, xb.z, xb.w);
+    }
 }
 
 __device__ __forceinline__ void mbar_arrive(void* bar)
@@ -262,6 +283,7 @@ __device__ __forceinline__ void mbar_arrive(void* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
@@ -300,8 +322,9 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
     unsigned char* zq_s = sc_s + GMAXC * SC_ROW;                                  // GMAXC x 64 (raw packed zeros)
     unsigned char* seg_s = zq_s + GMAXC * ZQ_ROW;                                 // GMAXC x 8 tokens x {sum x_q, x scale}
     float* red = reinterpret_cast<float*>(seg_s + SEG_BYTES);                     // WK x 8 x RED_LD
-    float* slots = red + WK * GV_MAXM * RED_LD;                                   // 2 x cs x M x 128 (cluster reduction)
-    unsigned char* xs = reinterpret_cast<unsigned char*>(slots + 2 * cs * M * GV_TILE_N);   // M x xs_stride
+    constexpr int NSUB_ = (EPI == GV_EPI_SILU_MUL) ? 2 : 1;
+    float* slots = red + WK * GV_MAXM * RED_LD;                                   // NSUB x cs x M x 128 (cluster reduction)
+    unsigned char* xs = reinterpret_cast<unsigned char*>(slots + NSUB_ * cs * M * GV_TILE_N);   // M x xs_stride
     __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST], sc_bar;
     __shared__ float s_rm[GV_MAXM];
     __shared__ float s_wsum[CONSUMERS / 32];
@@ -320,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    if (cs > 1) cluster_arrive();          // #0: "this CTA is running" -- waited on before the first DSMEM store
+    if (cs > 1) cluster_arrive_relaxed();  // #0: "this CTA is running" -- waited on before the first DSMEM store
 
     // resolve (item, sub) -> matrix + column tile
     auto resolve = [&](int sub, int& mi, int& ctile) {
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
         #pragma unroll
         for (int j = 0; j < 4; j++) A.cs[j] = 0.f;
         A.zp4 = 0; A.sxq[0] = A.sxq[1] = 0; A.sxs[0] = A.sxs[1] = 0.f;
-        A.cur_grp = -1;
+        A.cur_grp = -1; A.fresh = true;
 
         for (int c0 = sg0; c0 < sg1; c0 += a.chunk_stages) {
             const int c1 = min(sg1, c0 + a.chunk_stages);
@@ -419,6 +442,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                 }
             }
 
+            const bool reuse_x = (NSUB == 2) && sub > 0 && c0 == sg0 && c1 == sg1;   // same x, same quantisation: keep it
             if (!waited_dep) {
                 pdl_wait();                  // everything below may read x / write out
                 waited_dep = true;
@@ -448,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
             }
 
             // ---- stage x[:, c0*128 .. c1*128) into smem (pass 1: fp16 after the act-order gather / RMS norm) ----
-            {
+            if (!reuse_x) {
                 const int nk8 = (c1 - c0) * STAGE_ROWS;
                 const int k8_0 = c0 * STAGE_ROWS;
                 for (int idx = tid; idx < M * nk8; idx += CONSUMERS) {
@@ -489,9 +513,9 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                     *reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)j * 16) = xv;   // fp16, natural order (pass 1)
                 }
             }
-            consumer_sync();
+            if (!reuse_x) consumer_sync();
             // ---- pass 2: quantise each (token, segment) of the staged x to 16-bit integers with its own scale, in place ----
-            {
+            if (!reuse_x) {
                 const int nseg = g_hi - g_lo + 1;
                 const int rows_lo = c0 * STAGE_ROWS, rows_hi = min(c1 * STAGE_ROWS, k8_lim);
                 const int nrows = (c1 - c0) * STAGE_ROWS;
@@ -518,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                             const int r = rows_lo + rr;                       // absolute k8-row
                             if ((r & (rpg - 1)) == 0) {
                                 const int gi = r / rpg - g_lo;
-                                const int par = (jbase + (r / STAGE_ROWS - sg0)) & 1;   // k-warp that consumes this ring stage
+                                const int par = (r / STAGE_ROWS - sg0) & 1;             // parity of the stage inside this CTA's slice
                                 table[gi * GV_MAXM + m] = make_uint4(par ? 0u : (uint32_t)sum, par ? (uint32_t)sum : 0u,
                                                                      __float_as_uint(mx * (1.0f / 32767.0f)), 0u);
                             }
@@ -543,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                             uint4 q;
                             const int sm = quantise_row(*rp, inv, q);
                             *rp = q;
-                            if ((jbase + (r / STAGE_ROWS - sg0)) & 1) sum1 += sm; else sum0 += sm;
+                            if ((r / STAGE_ROWS - sg0) & 1) sum1 += sm; else sum0 += sm;
                         }
                         #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) { sum0 += __shfl_xor_sync(0xffffffffu, sum0, o); sum1 += __shfl_xor_sync(0xffffffffu, sum1, o); }
@@ -565,6 +589,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
             const uint32_t sc_a = smem_u32(sc_s), zq_a = smem_u32(zq_s), seg_a = smem_u32(seg_s);
             const bool tail_checks = (K % STAGE_K) != 0;       // only a ragged last stage needs per-unit bounds checks
             const bool skip_math = !col_ok || (a.debug & 5);
+            const int rel_par = (wk - jbase) & 1;              // slice-relative parity of the stages this k-warp consumes
             // first stage of this chunk that belongs to this k-warp: global stage counter parity == wk
             int sg = c0 + ((wk - (jbase + (c0 - sg0))) & 1);
             for (; sg < c1; sg += 2) {
@@ -582,7 +607,7 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
                     #define GV_UNIT(U_, W_, X_)                                                            \
                         if (!tail_checks || ((u0 + U_) * 4 + 4) <= k8_lim) {                               \
                             const int grp = (u0 + U_) >> a.gs_shift32;                                     \
-                            if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zq_a, seg_a, lane_col, t, wk); \
+                            if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zq_a, seg_a, lane_col, t, rel_par); \
                             unit_mma(A, W_, X_);                                                           \
                         }
                     GV_UNIT(0, w0, x0) GV_UNIT(1, w1, x1) GV_UNIT(2, w2, x2) GV_UNIT(3, w3, x3)
@@ -711,9 +736,10 @@ int launch_cfg(ExlDevice* ds, GemvArgs& a, int items, cudaStream_t stream)
     static int cap_mult = -1;
     if (cap_mult < 0) { const char* e = getenv("EXL_GV_CAP"); cap_mult = e ? atoi(e) : 2; }
     const int cap = ds->num_sms * cap_mult;
+    const int nsub = (EPI == GV_EPI_SILU_MUL) ? 2 : 1;
     auto smem_for = [&](int c) {
         return (size_t)1024 + (size_t)NST * STAGE_BYTES + (size_t)GMAXC * (SC_ROW + ZQ_ROW) + SEG_BYTES +
-               (size_t)WK * GV_MAXM * RED_LD * sizeof(float) + (size_t)2 * c * a.M * GV_TILE_N * sizeof(float) + (size_t)a.M * a.xs_stride;
+               (size_t)WK * GV_MAXM * RED_LD * sizeof(float) + (size_t)nsub * c * a.M * GV_TILE_N * sizeof(float) + (size_t)a.M * a.xs_stride;
     };
     // max co-resident clusters per cluster size, measured once per (device, M) with the occupancy API
     static int max_clusters[EXL_MAX_DEVICES][GV_MAXM + 1][MAX_CS + 1] = {};
@@ -734,11 +760,11 @@ int launch_cfg(ExlDevice* ds, GemvArgs& a, int items, cudaStream_t stream)
     int cs = 1;
     for (int c = MAX_CS; c > 1; c--) {
         if ((long long)items * c > cap || c > a.spt) continue;
-        if (2 * c * a.M * GV_TILE_N * (int)sizeof(float) > SLOT_BUDGET) continue;
+        if (nsub * c * a.M * GV_TILE_N * (int)sizeof(float) > SLOT_BUDGET) continue;
         if (clusters_fit(c) < items) continue;
         cs = c; break;
     }
-    if (force_cs >= 1 && force_cs <= MAX_CS && force_cs <= a.spt && 2 * force_cs * a.M * GV_TILE_N * (int)sizeof(float) <= SLOT_BUDGET) cs = force_cs;
+    if (force_cs >= 1 && force_cs <= MAX_CS && force_cs <= a.spt && nsub * force_cs * a.M * GV_TILE_N * (int)sizeof(float) <= SLOT_BUDGET) cs = force_cs;
     a.cs = cs;
     const size_t smem = smem_for(cs);
 
