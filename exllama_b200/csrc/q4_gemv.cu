@@ -33,6 +33,12 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef GV_MINB
+#define GV_MINB 2                    // resident CTAs per SM the register allocation is tuned for
+#endif
+#ifndef GV_GMAXC
+#define GV_GMAXC 32
+#endif
 #ifndef GV_NST
 #define GV_NST 6                    // TMA ring depth (stages of 16 k8-rows x 128 columns)
 #endif
@@ -48,8 +54,9 @@ constexpr int BOX_COLS = 32;                 // TMA box: 32 columns (128 B, SWIZ
 constexpr int BOX_BYTES = STAGE_ROWS * BOX_COLS * 4;
 constexpr int STAGE_BYTES = WN * BOX_BYTES;  // 8 KB
 constexpr int NST = GV_NST;
+static_assert(NST % 2 == 0, "the two k-warp groups alternate ring stages");
 constexpr int RED_LD = GV_TILE_N + 4;
-constexpr int GMAXC = 32;                  // max quantisation groups staged per chunk
+constexpr int GMAXC = GV_GMAXC;                  // max quantisation groups staged per chunk
 constexpr int SC_ROW = GV_TILE_N * 2;      // bytes of scales per group row in smem
 constexpr int ZQ_ROW = GV_TILE_N / 2;      // bytes of packed zeros per group row in smem (raw, as TMA delivers them)
 constexpr int SEG_BYTES = GMAXC * GV_MAXM * 16;  // per (segment, token): {sum of x_q over even ring stages, over odd ring stages, x scale, -}
@@ -313,7 +320,7 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int PRO, int EPI>
-__global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_constant__ GemvArgs a)
+__global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_constant__ GemvArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int cs = a.cs, M = a.M, K = a.K, spt = a.spt;
@@ -592,30 +599,57 @@ __global__ void __launch_bounds__(THREADS, 2) q4_gemv_kernel(const __grid_consta
             const int rel_par = (wk - jbase) & 1;              // slice-relative parity of the stages this k-warp consumes
             // first stage of this chunk that belongs to this k-warp: global stage counter parity == wk
             int sg = c0 + ((wk - (jbase + (c0 - sg0))) & 1);
+            // ring position of that stage; this warp then advances two stages at a time
+            int slot = (jbase + (sg - sg0)) % NST;
+            uint32_t phase = (uint32_t)((jbase + (sg - sg0)) / NST) & 1u;
+            uint32_t xb = xa0 + (uint32_t)(sg - c0) * (STAGE_ROWS * 16);
+            #define GV_UNIT_CHECKED(U_, W_, X_)                                                        \
+                if (((u0 + U_) * 4 + 4) <= k8_lim) {                                                   \
+                    const int grp = (u0 + U_) >> a.gs_shift32;                                         \
+                    if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zq_a, seg_a, lane_col, t, rel_par); \
+                    unit_mma(A, W_, X_);                                                               \
+                }
+            #define GV_UNIT_FAST(U_, W_, X_)                                                           \
+                {                                                                                      \
+                    const int grp = (u0 + U_) >> gshift;                                               \
+                    if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zq_a, seg_a, lane_col, t, rel_par); \
+                    unit_mma(A, W_, X_);                                                               \
+                }
+            const int gshift = a.gs_shift32;
             for (; sg < c1; sg += 2) {
-                const int j = jbase + (sg - sg0);                    // position in the ring sequence
-                const int slot = j % NST;
-                const uint32_t phase = (uint32_t)(j / NST) & 1u;
                 mbar_wait_a(full0 + slot * 8, phase);
                 if (!skip_math) {
                     const uint32_t wb = slot * STAGE_BYTES;
-                    const uint32_t xb = xa0 + (uint32_t)(sg - c0) * (STAGE_ROWS * 16);
-                    const uint4 w0 = lds128(wa_even + wb), w1 = lds128(wa_odd + wb);
-                    const uint4 w2 = lds128(wa_even + wb + 8 * 128), w3 = lds128(wa_odd + wb + 8 * 128);
-                    const uint4 x0 = lds128(xb), x1 = lds128(xb + 64), x2 = lds128(xb + 128), x3 = lds128(xb + 192);
                     const int u0 = sg * 4;
-                    #define GV_UNIT(U_, W_, X_)                                                            \
-                        if (!tail_checks || ((u0 + U_) * 4 + 4) <= k8_lim) {                               \
-                            const int grp = (u0 + U_) >> a.gs_shift32;                                     \
-                            if (grp != A.cur_grp) group_switch(A, grp, g_lo, sc_a, zq_a, seg_a, lane_col, t, rel_par); \
-                            unit_mma(A, W_, X_);                                                           \
+                    if (!tail_checks) {
+                        // two units at a time keeps the live register set small (no spills at 96 registers)
+                        {
+                            const uint4 w0 = lds128(wa_even + wb), w1 = lds128(wa_odd + wb);
+                            const uint4 x0 = lds128(xb), x1 = lds128(xb + 64);
+                            GV_UNIT_FAST(0, w0, x0) GV_UNIT_FAST(1, w1, x1)
                         }
-                    GV_UNIT(0, w0, x0) GV_UNIT(1, w1, x1) GV_UNIT(2, w2, x2) GV_UNIT(3, w3, x3)
-                    #undef GV_UNIT
+                        {
+                            const uint4 w2 = lds128(wa_even + wb + 8 * 128), w3 = lds128(wa_odd + wb + 8 * 128);
+                            const uint4 x2 = lds128(xb + 128), x3 = lds128(xb + 192);
+                            GV_UNIT_FAST(2, w2, x2) GV_UNIT_FAST(3, w3, x3)
+                        }
+                    } else {
+                        #pragma unroll 1
+                        for (int u = 0; u < 4; u++) {      // ragged last stage (K % 128 != 0): rare, keep it compact
+                            const uint4 wv = lds128(((u & 1) ? wa_odd : wa_even) + wb + (u >> 1) * 8 * 128);
+                            const uint4 xv = lds128(xb + u * 64);
+                            GV_UNIT_CHECKED(u, wv, xv)
+                        }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(empty0 + slot * 8);
+                xb += 2 * STAGE_ROWS * 16;
+                slot += 2;
+                if (slot >= NST) { slot -= NST; phase ^= 1u; }
             }
+            #undef GV_UNIT_CHECKED
+            #undef GV_UNIT_FAST
             // x scales are per (segment, chunk): close the open segment before the staging buffers are recycled
             if (A.cur_grp >= 0) { seg_flush(A); A.cur_grp = -1; }
         }
@@ -734,7 +768,7 @@ int launch_cfg(ExlDevice* ds, GemvArgs& a, int items, cudaStream_t stream)
     }
     // K split factor == cluster size: the largest (<= 8) that keeps every cluster of the launch co-resident.
     static int cap_mult = -1;
-    if (cap_mult < 0) { const char* e = getenv("EXL_GV_CAP"); cap_mult = e ? atoi(e) : 2; }
+    if (cap_mult < 0) { const char* e = getenv("EXL_GV_CAP"); cap_mult = e ? atoi(e) : GV_MINB; }
     const int cap = ds->num_sms * cap_mult;
     const int nsub = (EPI == GV_EPI_SILU_MUL) ? 2 : 1;
     auto smem_for = [&](int c) {
