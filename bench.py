@@ -177,6 +177,11 @@ def main():
 
     stack = DecodeStack(shape, groupsize=gs, act_order=False, device=str(dev), max_seq=args.seq,
                         tp_rank=rank, tp_size=world, tp_group=None)
+    fused_ar = False
+    if world > 1 and os.environ.get("EXL_TP_FUSED", "1") == "1":
+        from exllama_b200 import tp as tpmod, cuda_ext as _ce
+        tpmod.init_fused_allreduce(_ce.exllama_ext, dev.index)      # row-parallel projections: GEMV + peer-memory all-reduce in one kernel
+        fused_ar = True
     torch.cuda.synchronize()
 
     def barrier():
@@ -206,7 +211,8 @@ def main():
     torch.cuda.synchronize()
 
     graph = None
-    use_graph = not args.no_graph and (world == 1 or os.environ.get("EXL_BENCH_TP_GRAPH", "0") == "1")
+    # NCCL inside stream capture hung on this stack; the fused all-reduce kernels are plain launches and capture fine
+    use_graph = not args.no_graph and (world == 1 or fused_ar or os.environ.get("EXL_BENCH_TP_GRAPH", "0") == "1")
     if use_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -381,7 +387,7 @@ def main():
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{shape.name}-gptq4-g{gs}-noact decode token at ctx {past} of seq {args.seq}: {shape.layers} layers x "
                                    "(q4_attn, attention over KV cache, q4_attn_2, q4_mlp) + final norm + fp16 lm_head",
-                       "parallelism": f"tp{world}", "cuda_graph": graph is not None,
+                       "parallelism": f"tp{world}", "cuda_graph": graph is not None, "allreduce": ("fused GEMV epilogue over NVLink peer memory" if fused_ar else ("nccl" if world > 1 else None)),
                        "l2": "weights (3.6 GB/token) >> L2, every step streams them from HBM"},
             "e2e": {"value": round(1000.0 / e2e_ms, 2), "unit": "tok/s", "h2d_bytes_per_step": host_in.numel() * 2,
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(e2e_ms, 4), "mode": "eager plugin API"},

@@ -40,6 +40,11 @@ SIGNATURES = {
     "exl_q4_attn_2": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     "exl_q4_mlp": (i32, [vp, vp, f32, vp, vp, vp, i32, i32] + [vp, vp, i32] * 3 + [vp, i32, vp]),
     "exl_q4_attn_2_tp": (i32, [vp, vp, vp, i32, i32, vp]),
+    "exl_tp_workspace_alloc": (i32, [i32, C.POINTER(vp), vp]),
+    "exl_tp_workspace_open": (i32, [i32, vp, C.POINTER(vp)]),
+    "exl_tp_init": (i32, [i32, i32, i32, C.POINTER(vp)]),
+    "exl_q4_attn_2_ar": (i32, [vp, vp, vp, i32, vp]),
+    "exl_q4_mlp_ar": (i32, [vp, vp, f32, vp, vp, vp, i32, i32, i32, vp]),
     "exl_q4_mlp_tp": (i32, [vp, vp, f32, vp, vp, vp, i32, i32, i32, i32, vp]),
     "exl_rep_penalty": (i32, [i32, vp, vp, f32, i32, i32, i32]),
     "exl_apply_rep_penalty": (i32, [i32, vp, f32, i32, i32, i32, vp]),

@@ -414,7 +414,7 @@ int exl_q4_attn_2(void* x, const void* attn_output, const exl_q4_matrix* o_proj,
 static int q4_mlp_impl(void* x_, const void* rms_norm_weight, float epsilon, const exl_q4_matrix* gate, const exl_q4_matrix* up,
                const exl_q4_matrix* down, int height, int dim, const void* gate_a, const void* gate_b, int gate_rank,
                const void* up_a, const void* up_b, int up_rank, const void* down_a, const void* down_b, int down_rank,
-               void* lora_temp, int device, void* stream_, bool add_residual)
+               void* lora_temp, int device, void* stream_, bool add_residual, bool all_reduce = false)
 {
     if (!gate || !up || !down) return exl_set_err(EXL_ERR_STATE, "q4_mlp: NULL handle");
     ExlDevice* ds = exl_device_state(device);
@@ -442,8 +442,13 @@ static int q4_mlp_impl(void* x_, const void* rms_norm_weight, float epsilon, con
         GemvFused f; f.norm_w = (const half*)rms_norm_weight; f.eps = epsilon;
         int rc = exl_gemv_launch(ds, x, height, mats, outs, 2, false, GV_PRO_RMSNORM, GV_EPI_SILU_MUL, &f, stream);
         if (rc != EXL_OK) return rc;
+        if (all_reduce) {
+            half* o = x;
+            return exl_gemv_launch(ds, temp_mlp, height, &down, &o, 1, true, GV_PRO_PLAIN, GV_EPI_ALLREDUCE, nullptr, stream);
+        }
         return q4_matmul_dispatch(ds, temp_mlp, height, down, x, add_residual, 0, stream);
     }
+    if (all_reduce) return exl_set_err(EXL_ERR_ARG, "q4_mlp_ar: only the fused decode configuration (rows <= 8, no act-order mismatch) is supported");
 
     half* temp_x = have_norm ? ds->temp_state + (size_t)height * dim : own;
     half* t0 = temp_mlp; half* t1 = temp_mlp + (size_t)height * inter;
@@ -481,6 +486,63 @@ int exl_q4_mlp_tp(void* x, const void* rms_norm_weight, float epsilon, const exl
 {
     return q4_mlp_impl(x, rms_norm_weight, epsilon, gate, up, down, height, dim, nullptr, nullptr, 0, nullptr, nullptr, 0,
                        nullptr, nullptr, 0, nullptr, device, stream, add_residual != 0);
+}
+
+int exl_q4_mlp_ar(void* x, const void* rms_norm_weight, float epsilon, const exl_q4_matrix* gate, const exl_q4_matrix* up,
+                  const exl_q4_matrix* down, int height, int dim, int device, void* stream)
+{
+    return q4_mlp_impl(x, rms_norm_weight, epsilon, gate, up, down, height, dim, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                       nullptr, nullptr, 0, nullptr, device, stream, true, true);
+}
+
+int exl_q4_attn_2_ar(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, void* stream)
+{
+    if (!o_proj) return exl_set_err(EXL_ERR_STATE, "q4_attn_2_ar: NULL handle");
+    ExlDevice* ds = exl_device_state(o_proj->device);
+    if (!ds) return EXL_ERR_CUDA;
+    if (height > GV_MAXM) return exl_set_err(EXL_ERR_ARG, "q4_attn_2_ar: rows %d > %d", height, GV_MAXM);
+    DeviceGuard guard(o_proj->device);
+    half* o = (half*)x;
+    return exl_gemv_launch(ds, (const half*)attn_output, height, &o_proj, &o, 1, true, GV_PRO_PLAIN, GV_EPI_ALLREDUCE, nullptr, (cudaStream_t)stream);
+}
+
+int exl_tp_workspace_alloc(int device, void** local_ptr, void* ipc_handle)
+{
+    ExlDevice* ds = exl_device_state(device);
+    if (!ds) return EXL_ERR_CUDA;
+    DeviceGuard guard(device);
+    if (!ds->tp_local) {
+        EXL_CUDA_TRY(cudaMalloc(&ds->tp_local, TP_WS_BYTES));
+        EXL_CUDA_TRY(cudaMemset(ds->tp_local, 0, TP_WS_BYTES));
+        EXL_CUDA_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    EXL_CUDA_TRY(cudaIpcGetMemHandle(&h, ds->tp_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    memcpy(ipc_handle, &h, 64);
+    *local_ptr = ds->tp_local;
+    return EXL_OK;
+}
+
+int exl_tp_workspace_open(int device, const void* ipc_handle, void** peer_ptr)
+{
+    if (!exl_device_state(device)) return EXL_ERR_CUDA;
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    EXL_CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return EXL_OK;
+}
+
+int exl_tp_init(int device, int rank, int world, void* const* workspace_ptrs)
+{
+    ExlDevice* ds = exl_device_state(device);
+    if (!ds) return EXL_ERR_CUDA;
+    if (world < 1 || world > TP_MAX_RANKS || rank < 0 || rank >= world) return exl_set_err(EXL_ERR_ARG, "tp_init: bad rank %d / world %d", rank, world);
+    if (!ds->tp_local || workspace_ptrs[rank] != ds->tp_local) return exl_set_err(EXL_ERR_STATE, "tp_init: own workspace entry must be the pointer from exl_tp_workspace_alloc");
+    ds->tp_rank = rank; ds->tp_world = world;
+    for (int i = 0; i < TP_MAX_RANKS; i++) ds->tp_peers[i] = i < world ? (unsigned char*)workspace_ptrs[i] : nullptr;
+    return EXL_OK;
 }
 
 int exl_q4_attn_2_tp(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, int add_residual, void* stream)

@@ -59,7 +59,19 @@ struct ExlDevice
     half* own_norm = nullptr;  int64_t own_norm_numel = 0;   // scratch for fused ops when temp_state is absent
     cublasHandle_t blas = nullptr;
     int gemv_ctas_per_sm = 0;
+    // tensor-parallel one-shot all-reduce over NVLink peer memory (q4_gemv.cu, GV_EPI_ALLREDUCE)
+    int tp_rank = 0, tp_world = 1;
+    unsigned char* tp_local = nullptr;                 // this rank's workspace (cudaMalloc, exported through cudaIpc)
+    unsigned char* tp_peers[8] = {nullptr};            // every rank's workspace mapped into this process (own = tp_local)
 };
+
+// workspace layout (identical on every rank): receive slots [parity 2][src rank 8][tile TP_MAX_TILES][row 8][128] fp32,
+// flags [parity 2][src rank 8][tile] u32, then {epoch, done} u32
+constexpr int TP_MAX_RANKS = 8;
+constexpr int TP_MAX_TILES = 256;
+constexpr size_t TP_DATA_BYTES = (size_t)2 * TP_MAX_RANKS * TP_MAX_TILES * 8 * 128 * sizeof(float);
+constexpr size_t TP_FLAG_BYTES = (size_t)2 * TP_MAX_RANKS * TP_MAX_TILES * sizeof(unsigned);
+constexpr size_t TP_WS_BYTES = TP_DATA_BYTES + TP_FLAG_BYTES + 256;
 
 extern ExlTuning g_tuning;
 extern std::atomic<int64_t> g_launches;
@@ -97,7 +109,7 @@ struct DeviceGuard
 
 // q4_gemv.cu : skinny-M fused unpack + scale/zero + GEMV (M <= 8), up to 3 matrices sharing x.
 enum GemvPrologue { GV_PRO_PLAIN = 0, GV_PRO_RMSNORM = 1 };
-enum GemvEpilogue { GV_EPI_STORE = 0, GV_EPI_SILU_MUL = 1, GV_EPI_ROPE_CACHE = 2 };
+enum GemvEpilogue { GV_EPI_STORE = 0, GV_EPI_SILU_MUL = 1, GV_EPI_ROPE_CACHE = 2, GV_EPI_ALLREDUCE = 3 };
 
 struct GemvFused
 {

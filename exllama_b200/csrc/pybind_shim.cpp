@@ -7,6 +7,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <cstdint>
+#include <string>
+#include <vector>
 #include "../../include/exl_b200.h"
 
 #define STRINGIFY_(x) #x
@@ -252,6 +254,45 @@ void q4_mlp_tp(torch::Tensor x, torch::Tensor rms_norm_weight, float epsilon, ui
                            add_residual, device_index, cur_stream()));
 }
 
+// fused projection + peer-memory all-reduce
+pybind11::tuple tp_workspace_alloc(int device)
+{
+    void* p = nullptr; char h[64];
+    EXL_CALL(exl_tp_workspace_alloc(device, &p, h));
+    return pybind11::make_tuple(reinterpret_cast<uintptr_t>(p), pybind11::bytes(h, 64));
+}
+uintptr_t tp_workspace_open(int device, pybind11::bytes handle)
+{
+    std::string h = handle;
+    TORCH_CHECK(h.size() == 64, "ipc handle must be 64 bytes");
+    void* p = nullptr;
+    EXL_CALL(exl_tp_workspace_open(device, h.data(), &p));
+    return reinterpret_cast<uintptr_t>(p);
+}
+void tp_init(int device, int rank, int world, std::vector<uintptr_t> ptrs)
+{
+    std::vector<void*> v; for (auto p : ptrs) v.push_back(reinterpret_cast<void*>(p));
+    TORCH_CHECK((int)v.size() == world, "tp_init: need one workspace pointer per rank");
+    EXL_CALL(exl_tp_init(device, rank, world, v.data()));
+}
+void q4_attn_2_ar(torch::Tensor x, torch::Tensor attn_output, uintptr_t o_proj)
+{
+    CHECK_DTYPE(x, kHalf);
+    CHECK_DTYPE(attn_output, kHalf);
+    const at::cuda::OptionalCUDAGuard device_guard(x.device());
+    EXL_CALL(exl_q4_attn_2_ar(x.data_ptr(), attn_output.data_ptr(), H(o_proj), (int)x.size(0), cur_stream()));
+}
+void q4_mlp_ar(torch::Tensor x, torch::Tensor rms_norm_weight, float epsilon, uintptr_t gate, uintptr_t up, uintptr_t down)
+{
+    CHECK_DTYPE(x, kHalf);
+    CHECK_DTYPE(rms_norm_weight, kHalf);
+    const int device_index = x.device().index();
+    CHECK_DEVICE_INDEX(device_index);
+    const at::cuda::OptionalCUDAGuard device_guard(x.device());
+    EXL_CALL(exl_q4_mlp_ar(x.data_ptr(), rms_norm_weight.data_ptr(), epsilon, H(gate), H(up), H(down), (int)x.size(0), (int)x.size(1),
+                           device_index, cur_stream()));
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
     m.def("set_tuning_params", &set_tuning_params, "set_tuning_params");
@@ -273,4 +314,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     // additions for tensor parallelism
     m.def("q4_attn_2_tp", &q4_attn_2_tp, "q4_attn_2_tp");
     m.def("q4_mlp_tp", &q4_mlp_tp, "q4_mlp_tp");
+    m.def("tp_workspace_alloc", &tp_workspace_alloc, "tp_workspace_alloc");
+    m.def("tp_workspace_open", &tp_workspace_open, "tp_workspace_open");
+    m.def("tp_init", &tp_init, "tp_init");
+    m.def("q4_attn_2_ar", &q4_attn_2_ar, "q4_attn_2_ar");
+    m.def("q4_mlp_ar", &q4_mlp_ar, "q4_mlp_ar");
 }

@@ -88,6 +88,9 @@ struct alignas(64) GemvArgs
     int head_dim, num_heads, num_kv_heads, past_len, max_seq_len;
     half* key_cache; half* value_cache;
     int debug;                         // EXL_GV_DEBUG bitmask (profiling experiments only)
+    // GV_EPI_ALLREDUCE: one-shot all-reduce of the tile over NVLink peer memory
+    int tp_rank, tp_world;
+    unsigned char* tp_peers[8];
 };
 
 __device__ __forceinline__ float ldcg_f32(const float* p)
@@ -316,6 +319,18 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p)
+{
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p)
+{
+    float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -699,7 +714,63 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
         const int N = mi == 0 ? a.mats[0].N : (mi == 1 ? a.mats[1].N : a.mats[2].N);
         const int col_tile0 = ctile * GV_TILE_N;
         const int col = col_tile0 + ecol;
-        if (EPI == GV_EPI_STORE) {
+        if (EPI == GV_EPI_ALLREDUCE) {
+            // Row-parallel projection of a tensor-parallel layer: out += sum over ranks of this rank's partial tile.
+            // One-shot "push" all-reduce fused into the epilogue: the tile is stored straight into every peer's receive slot
+            // over NVLink (posted writes), a system-scope release flag follows, each rank then sums the W partials out of
+            // its OWN memory in rank order (bitwise identical result on every rank) and adds the residual it already holds.
+            __shared__ unsigned s_epoch;
+            const int W = a.tp_world, R = a.tp_rank;
+            unsigned* ctl = reinterpret_cast<unsigned*>(a.tp_peers[R] + TP_DATA_BYTES + TP_FLAG_BYTES);     // {epoch, done}
+            if (tid == 0) s_epoch = ld_acquire_sys_u32(ctl);        // after griddepcontrol.wait: the previous launch has bumped it
+            consumer_sync();
+            const unsigned epoch = s_epoch;
+            const int par = (int)(epoch & 1u);
+            const int tile_id = item;                                // one matrix: item == column tile
+            const size_t slot_me = (((size_t)par * TP_MAX_RANKS + R) * TP_MAX_TILES + tile_id) * 8 * GV_TILE_N;
+            for (int p = 0; p < W; p++) {
+                if (p == R) continue;
+                float* dst = reinterpret_cast<float*>(a.tp_peers[p]) + slot_me;
+                #pragma unroll
+                for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) dst[m * GV_TILE_N + ecol] = v[i]; }
+            }
+            __threadfence_system();
+            consumer_sync();
+            if (tid < W && tid != R) {
+                unsigned* pf = reinterpret_cast<unsigned*>(a.tp_peers[tid] + TP_DATA_BYTES) + ((size_t)par * TP_MAX_RANKS + R) * TP_MAX_TILES + tile_id;
+                st_release_sys_u32(pf, epoch + 1u);
+                const unsigned* mf = reinterpret_cast<const unsigned*>(a.tp_peers[R] + TP_DATA_BYTES) + ((size_t)par * TP_MAX_RANKS + tid) * TP_MAX_TILES + tile_id;
+                while (ld_acquire_sys_u32(mf) != epoch + 1u) { }
+            }
+            consumer_sync();
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int p = 0; p < W; p++) {
+                if (p == R) {
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) tot[i] += v[i];
+                } else {
+                    const float* src = reinterpret_cast<const float*>(a.tp_peers[R]) + (((size_t)par * TP_MAX_RANKS + p) * TP_MAX_TILES + tile_id) * 8 * GV_TILE_N;
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) tot[i] += ld_relaxed_sys_f32(src + m * GV_TILE_N + ecol); }
+                }
+            }
+            if (col < N) {
+                #pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int m = em0 + 2 * i;
+                    if (m < M) {
+                        half* o = outp + (size_t)m * N + col;
+                        *o = __float2half_rn(tot[i] + (a.no_zero ? __half2float(*o) : 0.f));
+                    }
+                }
+            }
+            // last tile of this launch bumps the epoch (device-side, so the launch sequence can live in a CUDA graph)
+            consumer_sync();
+            if (tid == 0) {
+                const unsigned done = atomicAdd(ctl + 1, 1u);
+                if (done == (unsigned)(gridDim.x / cs) - 1u) { ctl[1] = 0u; __threadfence(); st_release_sys_u32(ctl, epoch + 1u); }
+            }
+        } else if (EPI == GV_EPI_STORE) {
             if (col < N) {
                 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -871,6 +942,8 @@ int exl_gemv_launch(ExlDevice* ds, const half* x, int M, const exl_q4_matrix* co
     a.chunk_stages = chunk_stages;
     a.xs_stride = chunk_stages * STAGE_K * 2 + 64;
     if (const char* e = getenv("EXL_GV_DEBUG")) a.debug = atoi(e);
+    a.tp_rank = ds->tp_rank; a.tp_world = ds->tp_world;
+    for (int i = 0; i < 8; i++) a.tp_peers[i] = ds->tp_peers[i];
     if (fused) {
         a.norm_w = fused->norm_w; a.eps = fused->eps; a.r_dim = 1.0f / (float)w0->K;
         a.sin = fused->sin; a.cos = fused->cos; a.head_dim = fused->head_dim; a.num_heads = fused->num_heads;
@@ -878,6 +951,11 @@ int exl_gemv_launch(ExlDevice* ds, const half* x, int M, const exl_q4_matrix* co
         a.key_cache = fused->key_cache; a.value_cache = fused->value_cache;
     }
 
+    if (epilogue == GV_EPI_ALLREDUCE) {
+        if (ds->tp_world < 2 || !ds->tp_local) return exl_set_err(EXL_ERR_STATE, "q4_gemv: all-reduce epilogue needs exl_tp_init");
+        if (num_mats != 1 || items > TP_MAX_TILES) return exl_set_err(EXL_ERR_ARG, "q4_gemv: all-reduce epilogue: one matrix, <= %d tiles", TP_MAX_TILES);
+        return launch_cfg<GV_PRO_PLAIN, GV_EPI_ALLREDUCE>(ds, a, items, stream);
+    }
     if (prologue == GV_PRO_PLAIN && epilogue == GV_EPI_STORE) return launch_cfg<GV_PRO_PLAIN, GV_EPI_STORE>(ds, a, items, stream);
     if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_STORE) return launch_cfg<GV_PRO_RMSNORM, GV_EPI_STORE>(ds, a, items, stream);
     if (prologue == GV_PRO_RMSNORM && epilogue == GV_EPI_ROPE_CACHE) {

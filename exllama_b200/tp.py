@@ -72,6 +72,9 @@ def row_parallel_residual(ext, x, inp, q4, rank, group):
     """x (replicated, [M, hidden]) += all_reduce(inp_local . W_rowshard).
     Rank 0 folds the residual into its partial (no_zero accumulate, exactly q4_attn_2); the other ranks
     overwrite their copy of x with their partial, so one in-place all-reduce leaves x_old + sum(partials) everywhere."""
+    if _fused_ready and x.shape[0] <= 8:
+        ext.q4_attn_2_ar(x, inp, q4)           # GEMV + one-shot all-reduce + residual in ONE kernel (no NCCL)
+        return
     ext.q4_attn_2_tp(x, inp, q4, rank == 0)
     all_reduce(x, group)
 
@@ -79,5 +82,35 @@ def row_parallel_residual(ext, x, inp, q4, rank, group):
 def mlp_tp(ext, cuda_ext, x, L, eps, rank, group):
     """Tensor-parallel MLP block: the same two fused launches as the single-GPU q4_mlp ([norm -> gate,up -> silu*mul],
     [down]) on this rank's column / row shards, then ONE all-reduce of the [M, hidden] partial."""
+    if _fused_ready and x.shape[0] <= 8:
+        ext.q4_mlp_ar(x, L.ln2, eps, L.gate.q4, L.up.q4, L.down.q4)
+        return
     ext.q4_mlp_tp(x, L.ln2, eps, L.gate.q4, L.up.q4, L.down.q4, rank == 0)
     all_reduce(x, group)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused projection + all-reduce over NVLink peer memory (exl_q4_attn_2_ar / exl_q4_mlp_ar)
+# ---------------------------------------------------------------------------------------------------------------------
+
+_fused_ready = False
+
+
+def init_fused_allreduce(ext, device_index, group=None):
+    """Exchange the cudaIpc handles of the per-rank workspaces (through the process group) and install the peer table.
+    Afterwards the row-parallel projections need no NCCL call: their GEMV epilogue does the one-shot all-reduce itself."""
+    global _fused_ready
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    local_ptr, handle = ext.tp_workspace_alloc(device_index)
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle), group=group)
+    ptrs = [local_ptr if r == rank else ext.tp_workspace_open(device_index, handles[r]) for r in range(world)]
+    ext.tp_init(device_index, rank, world, ptrs)
+    dist.barrier(group)
+    _fused_ready = True
+    return ptrs
+
+
+def fused_ready():
+    return _fused_ready

@@ -158,6 +158,20 @@ int exl_q4_mlp_tp(void* x, const void* rms_norm_weight, float epsilon,
                   const exl_q4_matrix* gate, const exl_q4_matrix* up, const exl_q4_matrix* down,
                   int height, int dim, int add_residual, int device, void* stream);
 
+/* Fused projection + all-reduce over NVLink peer memory (one kernel: the GEMV epilogue pushes its tile into every peer's
+   receive slot, flags it, and sums the partials of all ranks in rank order -- no NCCL call, CUDA-graph capturable).
+   Setup, once per process and device: every rank allocates a workspace and exports it through cudaIpc, the 64-byte
+   handles are exchanged by the host (any transport), peers are opened, then exl_tp_init installs the pointer table. */
+int exl_tp_workspace_alloc(int device, void** local_ptr, void* ipc_handle_64bytes);
+int exl_tp_workspace_open(int device, const void* ipc_handle_64bytes, void** peer_ptr);
+int exl_tp_init(int device, int rank, int world, void* const* workspace_ptrs /* [world], own entry = local_ptr */);
+/* x += all_reduce_sum(attn_output_local . o_proj_rowshard)            (every rank ends with the same x) */
+int exl_q4_attn_2_ar(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, void* stream);
+/* x += all_reduce_sum(down_rowshard(silu(gate(n)) * up(n))),  n = rms_norm(x)   */
+int exl_q4_mlp_ar(void* x, const void* rms_norm_weight, float epsilon,
+                  const exl_q4_matrix* gate, const exl_q4_matrix* up, const exl_q4_matrix* down,
+                  int height, int dim, int device, void* stream);
+
 /* --- sampling helper (CPU, like the reference) --------------------------------- */
 
 /* cpu_func/rep_penalty.cpp:5-31 */
