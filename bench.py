@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--torch-attn", action="store_true", help="attention between q4_attn and q4_attn_2 with the reference's torch ops instead of csrc/decode_attn.cu")
     return ap.parse_args()
 
 
@@ -177,6 +178,7 @@ def main():
 
     stack = DecodeStack(shape, groupsize=gs, act_order=False, device=str(dev), max_seq=args.seq,
                         tp_rank=rank, tp_size=world, tp_group=None)
+    stack.fused_decode_attn = not args.torch_attn
     fused_ar = False
     if world > 1 and os.environ.get("EXL_TP_FUSED", "1") == "1":
         from exllama_b200 import tp as tpmod, cuda_ext as _ce
@@ -249,6 +251,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = 1000.0 / ms_per_step
+
+    # the same step with the reference's torch attention ops (model.py:395-409) between our launches, for comparison
+    torch_attn_ms = None
+    if world == 1 and graph is not None and stack.fused_decode_attn:
+        stack.fused_decode_attn = False
+        for _ in range(2): step_eager()
+        torch.cuda.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, capture_error_mode="thread_local"):
+            step_eager()
+        for _ in range(3): g2.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(16): g2.replay()
+        b.record(); torch.cuda.synchronize()
+        torch_attn_ms = a.elapsed_time(b) / 16
+        del g2
+        stack.fused_decode_attn = True
 
     # "best" case of the reference's benchmark: nearly empty context
     def time_ctx(p, n=16):
@@ -386,7 +406,7 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{shape.name}-gptq4-g{gs}-noact decode token at ctx {past} of seq {args.seq}: {shape.layers} layers x "
-                                   "(q4_attn, attention over KV cache, q4_attn_2, q4_mlp) + final norm + fp16 lm_head",
+                                   "(q4_attn, " + ("decode_attn kernel" if stack.fused_decode_attn else "torch attention ops") + " over the KV cache, q4_attn_2, q4_mlp) + final norm + fp16 lm_head",
                        "parallelism": f"tp{world}", "cuda_graph": graph is not None, "allreduce": ("fused GEMV epilogue over NVLink peer memory" if fused_ar else ("nccl" if world > 1 else None)),
                        "l2": "weights (3.6 GB/token) >> L2, every step streams them from HBM"},
             "e2e": {"value": round(1000.0 / e2e_ms, 2), "unit": "tok/s", "h2d_bytes_per_step": host_in.numel() * 2,
@@ -398,6 +418,8 @@ def main():
             "kernels": kern_rows,
             "cpu_baseline": cpu,
             "prefill": prefill,
+            "decode_torch_attention": {"value": round(1000.0 / torch_attn_ms, 2), "unit": "tok/s", "mode": "cuda graph",
+                                       "note": "same step with the reference's torch attention ops instead of decode_attn"} if torch_attn_ms else None,
             "decode_best_ctx4": {"value": round(1000.0 / best_ms, 2), "unit": "tok/s", "mode": "eager"} if best_ms else None,
             "q4_weight_bytes_per_token": stack.q4_weight_bytes_per_token(),
             "weights_only_bound_tok_s": round(hbm_peak * 1e9 / (stack.q4_weight_bytes_per_token() + shape.vocab * shape.hidden * 2), 1),

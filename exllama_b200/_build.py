@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_SO = os.path.join(HERE, "libexl_b200.so")
 EXT_SO = os.path.join(HERE, "exllama_ext.so")
 
-CU_SOURCES = ["capi.cu", "q4_gemv.cu", "q4_matrix.cu", "elementwise.cu", "half_matmul.cu", "q4_gemm_tc.cu"]
+CU_SOURCES = ["capi.cu", "q4_gemv.cu", "q4_matrix.cu", "elementwise.cu", "half_matmul.cu", "q4_gemm_tc.cu", "decode_attn.cu"]
 HEADERS = ["exl_common.cuh", os.path.join("..", "..", "include", "exl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
@@ -50,7 +50,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             out, _ = p.communicate()
             if p.returncode != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out.decode())
-        cmd = [NVCC, "-shared", "-o", LIB_SO] + objs + ["-lcublas"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_SO] + objs + ["-lcublas"]
         subprocess.check_call(cmd)
     return LIB_SO
 

@@ -39,6 +39,7 @@ SIGNATURES = {
                     [vp, vp, i32] * 3 + [vp, i32, vp]),
     "exl_q4_attn_2": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     "exl_q4_mlp": (i32, [vp, vp, f32, vp, vp, vp, i32, i32] + [vp, vp, i32] * 3 + [vp, i32, vp]),
+    "exl_decode_attn": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "exl_q4_attn_2_tp": (i32, [vp, vp, vp, i32, i32, vp]),
     "exl_tp_workspace_alloc": (i32, [i32, C.POINTER(vp), vp]),
     "exl_tp_workspace_open": (i32, [i32, vp, C.POINTER(vp)]),
@@ -185,6 +186,13 @@ def q4_attn_2(x, attn_output, op: Q4):
 def q4_mlp(x, rms_w, eps, gate: Q4, up: Q4, down: Q4):
     check(lib().exl_q4_mlp(_ptr(x), _ptr(rms_w), eps, gate.handle, up.handle, down.handle, x.shape[0], x.shape[1],
                            None, None, 0, None, None, 0, None, None, 0, None, x.device.index or 0, _stream()))
+
+
+def decode_attn(q, key_cache, value_cache, num_heads, num_kv_heads, head_dim, seq_len, max_seq_len):
+    import torch
+    out = torch.empty_like(q)
+    check(lib().exl_decode_attn(_ptr(q), _ptr(key_cache), _ptr(value_cache), _ptr(out), num_heads, num_kv_heads, head_dim, seq_len, max_seq_len, _stream()))
+    return out
 
 
 def prepare_buffers(device, temp_state, temp_mlp, temp_zeros_float, temp_dq):

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <cstring>
 #include <cstdlib>
+#include <cmath>
 
 ExlTuning g_tuning;
 std::atomic<int64_t> g_launches{0};
@@ -552,6 +553,13 @@ int exl_q4_attn_2_tp(void* x, const void* attn_output, const exl_q4_matrix* o_pr
     if (!ds) return EXL_ERR_CUDA;
     DeviceGuard guard(o_proj->device);
     return q4_matmul_dispatch(ds, (const half*)attn_output, height, o_proj, (half*)x, add_residual != 0, 0, (cudaStream_t)stream);
+}
+
+int exl_decode_attn(const void* q, const void* key_cache, const void* value_cache, void* out, int num_heads, int num_kv_heads,
+                    int head_dim, int seq_len, int max_seq_len, void* stream)
+{
+    return exl_decode_attn_launch((const half*)q, (const half*)key_cache, (const half*)value_cache, (half*)out, num_heads, num_kv_heads,
+                                  head_dim, seq_len, max_seq_len, 1.0f / sqrtf((float)head_dim), (cudaStream_t)stream);
 }
 
 int exl_q4_matmul_host(const void* x_host, int M, const exl_q4_matrix* w, void* out_host, void* d_x, void* d_out, void* stream_)

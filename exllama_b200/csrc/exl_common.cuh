@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstring>
 #include <atomic>
 #include "../../include/exl_b200.h"
 
@@ -139,6 +140,10 @@ int exl_rope_launch(half* x, const half* sin, const half* cos, int bsz, int rows
 int exl_silu_mul_launch(half* x, const half* y, int height, int width, cudaStream_t stream);
 int exl_update_cache_launch(const half* k, const half* v, half* kc, half* vc, int head_dim, int kvh, int q_len, int max_seq, int past_len, cudaStream_t stream);
 int exl_column_remap_launch(const half* x, half* x_new, int M, int K, const uint32_t* x_map, cudaStream_t stream);
+
+// decode_attn.cu
+int exl_decode_attn_launch(const half* q, const half* kc, const half* vc, half* out, int heads, int kv_heads, int head_dim,
+                           int seq, int max_seq, float scale, cudaStream_t stream);
 
 // half_matmul.cu
 int exl_half_matmul_cublas_launch(ExlDevice* ds, const half* x, const half* w, half* out, int M, int K, int N, bool no_zero, cudaStream_t stream);

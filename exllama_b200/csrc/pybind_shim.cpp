@@ -254,6 +254,17 @@ void q4_mlp_tp(torch::Tensor x, torch::Tensor rms_norm_weight, float epsilon, ui
                            add_residual, device_index, cur_stream()));
 }
 
+// decode attention over the KV cache (one token): q [1, 1, heads*hd] -> out [1, 1, heads*hd]
+void decode_attn(torch::Tensor q, torch::Tensor key_cache, torch::Tensor value_cache, torch::Tensor out, int num_heads,
+                 int num_kv_heads, int head_dim, int seq_len, int max_seq_len)
+{
+    CHECK_DTYPE(q, kHalf); CHECK_DTYPE(key_cache, kHalf); CHECK_DTYPE(value_cache, kHalf); CHECK_DTYPE(out, kHalf);
+    TORCH_CHECK(q.numel() == (int64_t)num_heads * head_dim && out.numel() == q.numel(), "decode_attn handles one token");
+    const at::cuda::OptionalCUDAGuard device_guard(q.device());
+    EXL_CALL(exl_decode_attn(q.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(), out.data_ptr(), num_heads, num_kv_heads,
+                             head_dim, seq_len, max_seq_len, cur_stream()));
+}
+
 // fused projection + peer-memory all-reduce
 pybind11::tuple tp_workspace_alloc(int device)
 {
@@ -314,6 +325,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     // additions for tensor parallelism
     m.def("q4_attn_2_tp", &q4_attn_2_tp, "q4_attn_2_tp");
     m.def("q4_mlp_tp", &q4_mlp_tp, "q4_mlp_tp");
+    m.def("decode_attn", &decode_attn, "decode_attn");
     m.def("tp_workspace_alloc", &tp_workspace_alloc, "tp_workspace_alloc");
     m.def("tp_workspace_open", &tp_workspace_open, "tp_workspace_open");
     m.def("tp_init", &tp_init, "tp_init");

@@ -91,6 +91,7 @@ class DecodeStack:
         self.max_seq = max_seq
         self.n_layers = layers if layers is not None else shape.layers
         self.tp_rank, self.tp_size, self.tp_group = tp_rank, tp_size, tp_group
+        self.fused_decode_attn = True          # csrc/decode_attn.cu instead of the torch ops of model.py:395-409
         if act_order and tp_size > 1:
             raise NotImplementedError("tensor parallel + act-order needs the x_map exchange (SURVEY.md 8e hazard 1)")
         plan = tpmod.plan_shards(shape.hidden, shape.inter, shape.heads, shape.head_dim, groupsize, tp_size)
@@ -154,13 +155,19 @@ class DecodeStack:
             ext.q4_attn(hidden, L.ln1, s.eps, q, k, v, L.q.q4, L.k.q4, L.v.q4, self.sin, self.cos, q_len, past_len,
                         self.local_heads, self.local_heads, s.head_dim, self.key_cache[i], self.value_cache[i], self.max_seq,
                         none, none, none, none, none, none, none)
-            q = q.view(bsz, q_len, self.local_heads, s.head_dim).transpose(1, 2)
-            keys = self.key_cache[i].narrow(2, 0, past_len + q_len)
-            values = self.value_cache[i].narrow(2, 0, past_len + q_len)
-            attn = torch.matmul(q, keys.transpose(2, 3))
-            attn /= math.sqrt(s.head_dim)
-            attn = torch.nn.functional.softmax(attn, dim=-1, dtype=torch.float16)
-            attn = torch.matmul(attn, values).transpose(1, 2).reshape(bsz, q_len, hq)
+            if self.fused_decode_attn and q_len == 1 and s.head_dim == 128:
+                # one kernel over the KV cache instead of the five torch launches below (csrc/decode_attn.cu)
+                attn = torch.empty_like(q)
+                ext.decode_attn(q, self.key_cache[i], self.value_cache[i], attn, self.local_heads, self.local_heads,
+                                s.head_dim, past_len + 1, self.max_seq)
+            else:
+                q = q.view(bsz, q_len, self.local_heads, s.head_dim).transpose(1, 2)
+                keys = self.key_cache[i].narrow(2, 0, past_len + q_len)
+                values = self.value_cache[i].narrow(2, 0, past_len + q_len)
+                attn = torch.matmul(q, keys.transpose(2, 3))
+                attn /= math.sqrt(s.head_dim)
+                attn = torch.nn.functional.softmax(attn, dim=-1, dtype=torch.float16)
+                attn = torch.matmul(attn, values).transpose(1, 2).reshape(bsz, q_len, hq)
             x2 = hidden.view(-1, s.hidden)
             if self.tp_size == 1:
                 ext.q4_attn_2(x2, attn.view(-1, hq), L.o.q4, none, none, none)

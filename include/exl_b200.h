@@ -148,6 +148,14 @@ int exl_q4_mlp(void* x, const void* rms_norm_weight, float epsilon,
                const void* down_a, const void* down_b, int down_rank,
                void* lora_temp, int device, void* stream);
 
+/* --- decode attention (the ranked-first "next" row; not part of the reference's extension) ------------ */
+
+/* Single-query attention over the KV cache, replacing the torch ops of ExLlamaAttention.fused (model.py:372-409):
+   out[h, :] = softmax(q[h] . K[kvh(h), 0:seq]^T / sqrt(head_dim)) . V[kvh(h), 0:seq]      (fp32 arithmetic, fp16 in/out)
+   q, out: half [num_heads * head_dim] (one token); caches: half [num_kv_heads, max_seq_len, head_dim]; head_dim == 128. */
+int exl_decode_attn(const void* q, const void* key_cache, const void* value_cache, void* out,
+                    int num_heads, int num_kv_heads, int head_dim, int seq_len, int max_seq_len, void* stream);
+
 /* --- tensor-parallel variants (new functionality; the reference has no tensor parallelism) ----- */
 
 /* As exl_q4_attn_2 / exl_q4_mlp, but with add_residual == 0 the row-parallel projection OVERWRITES x with this rank's

@@ -218,6 +218,14 @@ def update_cache(key, value, key_cache, value_cache, head_dim, kvh, q_len, max_s
     return kc.view(np.float16).reshape(key_cache.shape), vc.view(np.float16).reshape(value_cache.shape)
 
 
+def decode_attn_f64(q, key_cache, value_cache, heads, kv_heads, head_dim, seq, max_seq, fp16_steps=False) -> np.ndarray:
+    """model.py:372-409 for one token; q [heads*hd] fp16, caches [kv_heads, max_seq, hd] fp16 -> float64 [heads*hd]."""
+    out = np.zeros(heads * head_dim, dtype=np.float64)
+    lib().orc_decode_attn(_p(_h(q)), _p(_h(key_cache)), _p(_h(value_cache)), _p(out), _i(heads), _i(kv_heads), _i(head_dim),
+                          _i(seq), _i(max_seq), _i(1 if fp16_steps else 0))
+    return out
+
+
 def rep_penalty(vocab_size, sequence, penalty_max, sustain, decay, use_ref=False) -> np.ndarray:
     seq = np.ascontiguousarray(sequence, dtype=np.int64).reshape(-1).view(np.uint64)
     mask = np.empty(vocab_size, dtype=np.float32)

@@ -221,3 +221,53 @@ def test_pybind_surface_end_to_end(oracle):
     lora = oracle.half_matmul_f64(xa, B).astype(np.float16)
     want = oracle.ref64_with_act_order(x, qw, qz, sc, g_idx, acc_in=lora)
     assert_close_ref64(out, want, rel=4e-3, rms=4e-3, what="lora")
+
+
+# ---- decode attention over the KV cache (model.py:372-409) --------------------------------------------------
+@pytest.mark.parametrize("heads,kv_heads,seq,max_seq", [
+    (32, 32, 1, 2048), (32, 32, 255, 2048), (32, 32, 257, 2048), (32, 32, 1921, 2048), (4, 4, 2048, 2048),
+    (8, 2, 300, 512), (64, 8, 1000, 1024), (2, 1, 3001, 4096), (40, 40, 777, 2048)])
+def test_decode_attn(oracle, heads, kv_heads, seq, max_seq):
+    import torch
+    from exllama_b200 import capi
+    hd = 128
+    rng = np.random.default_rng(heads * 7 + seq)
+    q = rng.standard_normal(heads * hd).astype(np.float16)
+    kc = rng.standard_normal((kv_heads, max_seq, hd)).astype(np.float16)
+    vc = rng.standard_normal((kv_heads, max_seq, hd)).astype(np.float16)
+    # a few dominant keys so the softmax is not flat (exercises the running-max rescale across splits / sub-blocks)
+    for h in range(kv_heads):
+        kc[h, rng.integers(0, seq)] *= 4
+    want = oracle.decode_attn_f64(q, kc, vc, heads, kv_heads, hd, seq, max_seq)
+    tq, tk, tv = to_cuda(q, kc, vc)
+    got = capi.decode_attn(tq, tk, tv, heads, kv_heads, hd, seq, max_seq).cpu().numpy()
+    # fp32 arithmetic, fp16 output: the final rounding (2^-11) dominates
+    assert_close_ref64(got, want, rel=1.5e-3, rms=1.5e-3, what="decode_attn")
+    # and it is closer to the exact answer than the reference's regular-attention branch with its fp16 rounding points
+    ref16 = oracle.decode_attn_f64(q, kc, vc, heads, kv_heads, hd, seq, max_seq, fp16_steps=True)
+    assert np.abs(got - want).max() <= np.abs(ref16 - want).max() + 2e-3 * np.abs(want).max()
+    # against the torch ops of model.py:395-409 on the same cache (what the kernel replaces)
+    rep = heads // kv_heads
+    qq = tq.view(1, 1, heads, hd).transpose(1, 2)
+    keys = tk[None, :, :seq].repeat_interleave(rep, dim=1)
+    vals = tv[None, :, :seq].repeat_interleave(rep, dim=1)
+    w = torch.matmul(qq, keys.transpose(2, 3))
+    w /= np.sqrt(hd)
+    w = torch.nn.functional.softmax(w, dim=-1, dtype=torch.float16)
+    tref = torch.matmul(w, vals).transpose(1, 2).reshape(-1).float().cpu().numpy()
+    assert np.abs(got.astype(np.float64) - tref).max() <= 4e-3 * max(1.0, np.abs(want).max())
+
+
+def test_decode_attn_errors():
+    from exllama_b200 import capi
+    import torch
+    q = torch.zeros(4 * 64, dtype=torch.float16, device="cuda")
+    kc = torch.zeros((4, 16, 64), dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError, match="head_dim"):
+        capi.decode_attn(q, kc, kc, 4, 4, 64, 1, 16)
+    q = torch.zeros(4 * 128, dtype=torch.float16, device="cuda")
+    kc = torch.zeros((4, 16, 128), dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError, match="seq"):
+        capi.decode_attn(q, kc, kc, 4, 4, 128, 17, 16)
+    with pytest.raises(RuntimeError, match="head counts"):
+        capi.decode_attn(q, kc, kc, 4, 3, 128, 1, 16)

@@ -117,3 +117,21 @@ def test_rope_rotation_property(oracle):
     # position 0 with past_len 0 is the identity (cos=1, sin=0)
     y0 = oracle.rope(x[:, :heads], sin, cos, 1, heads, hd, heads, 0)
     np.testing.assert_array_equal(y0, x[:, :heads])
+
+
+def test_decode_attn_against_torch_fixture(oracle):
+    """oracle.decode_attn_f64 against the reference's attention tensor program run with torch on the CPU
+    (tests/golden/decode_attn_torch.npz, generated by oracle/gen_golden_attn.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "decode_attn_torch.npz"))
+    for i in range(int(g["n_cases"])):
+        heads, kvh, hd, seq, max_seq = (int(v) for v in g[f"shape_{i}"])
+        kc = np.zeros((kvh, max_seq, hd), np.float16); vc = np.zeros_like(kc)
+        kc[:, :seq], vc[:, :seq] = g[f"kc_{i}"], g[f"vc_{i}"]
+        exact = oracle.decode_attn_f64(g[f"q_{i}"], kc, vc, heads, kvh, hd, seq, max_seq)
+        np.testing.assert_allclose(exact, g[f"f32_{i}"], rtol=0, atol=3e-6 * max(1.0, np.abs(exact).max()) + 2e-6)
+        # the fp16 branch: same rounding points, torch accumulates its fp16 GEMMs in fp32 -> agree to an fp16 ulp or so
+        r16 = oracle.decode_attn_f64(g[f"q_{i}"], kc, vc, heads, kvh, hd, seq, max_seq, fp16_steps=True)
+        scale = max(1.0, np.abs(exact).max())
+        assert np.abs(r16 - g[f"f16_{i}"]).max() <= 3e-3 * scale
+        assert np.abs(r16 - exact).max() <= 5e-3 * scale
