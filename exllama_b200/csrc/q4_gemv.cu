@@ -304,6 +304,12 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)
 {
     asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
 }
+// st.async: a DSMEM store that completes tx bytes on an mbarrier of the destination CTA -- the data is visible to whoever
+// observes that barrier's phase flip, so no cluster-scope release fence (MEMBAR.GPU) is needed on the sending side
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" :: "r"(addr), "f"(v), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
 {
     uint4 r;
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
     constexpr int NSUB_ = (EPI == GV_EPI_SILU_MUL) ? 2 : 1;
     float* slots = red + WK * GV_MAXM * RED_LD;                                   // NSUB x cs x M x 128 (cluster reduction)
     unsigned char* xs = reinterpret_cast<unsigned char*>(slots + NSUB_ * cs * M * GV_TILE_N);   // M x xs_stride
-    __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST], sc_bar;
+    __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST], sc_bar, red_bar[2];
     __shared__ float s_rm[GV_MAXM];
     __shared__ float s_wsum[CONSUMERS / 32];
 
@@ -362,6 +368,12 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
         #pragma unroll
         for (int i = 0; i < NST; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], WN); }
         mbar_init(&sc_bar, 1);
+        // split-K partials of the other cs-1 CTAs land in this (leader) CTA's slots through st.async, counted in bytes
+        #pragma unroll
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&red_bar[i], 1);
+            if (cs > 1 && rank == 0) mbar_expect_tx(&red_bar[i], (uint32_t)(cs - 1) * (uint32_t)M * GV_TILE_N * 4u);
+        }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -399,9 +411,7 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
                 if (++pslot == NST) { pslot = 0; pphase ^= 1u; }
             }
             if (sub == NSUB - 1) pdl_launch_dependents();     // every weight byte of this CTA has been requested
-            if (cs > 1) { cluster_wait(); cluster_arrive(); }
         }
-        if (cs > 1) cluster_wait();
         return;
     }
 
@@ -419,10 +429,9 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
     float v[4] = {0.f, 0.f, 0.f, 0.f}, vprev[4] = {0.f, 0.f, 0.f, 0.f};
     int mi = 0, ctile = 0;
 
+    // o holds the leader's own partial on entry; the other ranks' partials are added in rank order (deterministic)
     auto sum_slots = [&](int buf, float (&o)[4]) {
-        #pragma unroll
-        for (int i = 0; i < 4; i++) o[i] = 0.f;
-        for (int r = 0; r < cs; r++) {
+        for (int r = 1; r < cs; r++) {
             const float* sp = slots + ((size_t)(buf * cs + r) * M) * GV_TILE_N;
             #pragma unroll
             for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) o[i] += sp[m * GV_TILE_N + ecol]; }
@@ -466,6 +475,13 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
 
             const bool reuse_x = (NSUB == 2) && sub > 0 && c0 == sg0 && c1 == sg1;   // same x, same quantisation: keep it
             if (!waited_dep) {
+                if (PRO == GV_PRO_RMSNORM && !a.x_map) {
+                    // the norm weights are constants: pull this thread's rows towards L1 while the previous kernel drains
+                    for (int idx = tid; idx < (c1 - c0) * STAGE_ROWS; idx += CONSUMERS) {
+                        const int k8 = c0 * STAGE_ROWS + idx;
+                        if (k8 < k8_lim) asm volatile("prefetch.global.L1 [%0];" :: "l"(a.norm_w + (size_t)k8 * 8));
+                    }
+                }
                 pdl_wait();                  // everything below may read x / write out
                 waited_dep = true;
                 if (PRO == GV_PRO_RMSNORM) {
@@ -493,50 +509,46 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
                 }
             }
 
-            // ---- stage x[:, c0*128 .. c1*128) into smem (pass 1: fp16 after the act-order gather / RMS norm) ----
-            if (!reuse_x) {
-                const int nk8 = (c1 - c0) * STAGE_ROWS;
-                const int k8_0 = c0 * STAGE_ROWS;
-                for (int idx = tid; idx < M * nk8; idx += CONSUMERS) {
-                    const int m = idx / nk8, j = idx - m * nk8;
-                    const int k8 = k8_0 + j;
-                    uint4 xv = make_uint4(0, 0, 0, 0);
-                    if (k8 < k8_lim) {
-                        const half* xr = a.x + (size_t)m * K;
+            // ---- stage x[:, c0*128 .. c1*128) into smem: one k8-row (8 values) of one token per thread ----
+            // fp16 after the act-order gather / RMS norm, exactly as the reference's separate kernels produce it
+            const int k8_0 = c0 * STAGE_ROWS;
+            auto stage_row = [&](int m, int j) -> uint4 {
+                const int k8 = k8_0 + j;
+                uint4 xv = make_uint4(0, 0, 0, 0);
+                if (k8 < k8_lim) {
+                    const half* xr = a.x + (size_t)m * K;
+                    if (a.x_map) {
+                        const uint32_t* mp = a.x_map + (size_t)k8 * 8;
+                        unsigned short h[8];
+                        #pragma unroll
+                        for (int i = 0; i < 8; i++) h[i] = __half_as_ushort(xr[mp[i]]);
+                        xv.x = h[0] | ((uint32_t)h[1] << 16); xv.y = h[2] | ((uint32_t)h[3] << 16);
+                        xv.z = h[4] | ((uint32_t)h[5] << 16); xv.w = h[6] | ((uint32_t)h[7] << 16);
+                    } else {
+                        xv = *reinterpret_cast<const uint4*>(xr + (size_t)k8 * 8);
+                    }
+                    if (PRO == GV_PRO_RMSNORM) {
+                        // (x * rm) * w with two fp16 multiplies, as rms_norm_kernel (rms_norm.cu:118-131)
+                        const half2 rm2 = __float2half2_rn(s_rm[m]);
+                        half2* hv = reinterpret_cast<half2*>(&xv);
                         if (a.x_map) {
                             const uint32_t* mp = a.x_map + (size_t)k8 * 8;
-                            unsigned short h[8];
                             #pragma unroll
-                            for (int i = 0; i < 8; i++) h[i] = __half_as_ushort(xr[mp[i]]);
-                            xv.x = h[0] | ((uint32_t)h[1] << 16); xv.y = h[2] | ((uint32_t)h[3] << 16);
-                            xv.z = h[4] | ((uint32_t)h[5] << 16); xv.w = h[6] | ((uint32_t)h[7] << 16);
-                        } else {
-                            xv = *reinterpret_cast<const uint4*>(xr + (size_t)k8 * 8);
-                        }
-                        if (PRO == GV_PRO_RMSNORM) {
-                            // (x * rm) * w with two fp16 multiplies, as rms_norm_kernel (rms_norm.cu:118-131)
-                            const half2 rm2 = __float2half2_rn(s_rm[m]);
-                            half2* hv = reinterpret_cast<half2*>(&xv);
-                            if (a.x_map) {
-                                const uint32_t* mp = a.x_map + (size_t)k8 * 8;
-                                #pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    half2 w2 = __halves2half2(a.norm_w[mp[2 * i]], a.norm_w[mp[2 * i + 1]]);
-                                    hv[i] = __hmul2(__hmul2(hv[i], rm2), w2);
-                                }
-                            } else {
-                                uint4 wv = *reinterpret_cast<const uint4*>(a.norm_w + (size_t)k8 * 8);
-                                const half2* w2 = reinterpret_cast<const half2*>(&wv);
-                                #pragma unroll
-                                for (int i = 0; i < 4; i++) hv[i] = __hmul2(__hmul2(hv[i], rm2), w2[i]);
+                            for (int i = 0; i < 4; i++) {
+                                half2 w2 = __halves2half2(a.norm_w[mp[2 * i]], a.norm_w[mp[2 * i + 1]]);
+                                hv[i] = __hmul2(__hmul2(hv[i], rm2), w2);
                             }
+                        } else {
+                            uint4 wv = *reinterpret_cast<const uint4*>(a.norm_w + (size_t)k8 * 8);
+                            const half2* w2 = reinterpret_cast<const half2*>(&wv);
+                            #pragma unroll
+                            for (int i = 0; i < 4; i++) hv[i] = __hmul2(__hmul2(hv[i], rm2), w2[i]);
                         }
                     }
-                    *reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)j * 16) = xv;   // fp16, natural order (pass 1)
                 }
-            }
-            if (!reuse_x) consumer_sync();
-            // ---- pass 2: quantise each (token, segment) of the staged x to 16-bit integers with its own scale, in place ----
+                return xv;
+            };
+            // ---- quantise each (token, segment) of x to 16-bit integers with its own scale ----
             if (!reuse_x) {
                 const int nseg = g_hi - g_lo + 1;
                 const int rows_lo = c0 * STAGE_ROWS, rows_hi = min(c1 * STAGE_ROWS, k8_lim);
@@ -553,7 +565,7 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
                         const bool act = idx < M * nrows;
                         const int m = act ? idx / nrows : 0, rr = act ? idx - m * nrows : 0;
                         uint4* rp = reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)rr * 16);
-                        const uint4 hv = act ? *rp : make_uint4(0, 0, 0, 0);
+                        const uint4 hv = act ? stage_row(m, rr) : make_uint4(0, 0, 0, 0);      // straight from registers: no fp16 round trip
                         float mx = row_absmax(hv);
                         for (int o = rpg >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                         uint4 q;
@@ -571,7 +583,12 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
                         }
                     }
                 } else {
-                    // large groups (groupsize >= 256 or a single group): one warp per (segment, token)
+                    // large groups (groupsize >= 256 or a single group): stage fp16 first, then one warp per (segment, token)
+                    for (int idx = tid; idx < M * nrows; idx += CONSUMERS) {
+                        const int m = idx / nrows, j = idx - m * nrows;
+                        *reinterpret_cast<uint4*>(xs + (size_t)m * a.xs_stride + (size_t)j * 16) = stage_row(m, j);
+                    }
+                    consumer_sync();
                     for (int task = warp; task < nseg * M; task += CONSUMERS / 32) {
                         const int gi = task / M, m = task - gi * M;
                         int r_lo = rows_lo, r_hi = rows_hi;
@@ -691,20 +708,29 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
 
         if (cs > 1) {
             // ---- cluster split-K: deposit the partial in the leader's slot [sub][rank] through DSMEM ----
-            cluster_wait();                                   // barrier #sub complete: leader is up / previous slots consumed
-            if (NSUB == 2 && sub == 1 && rank == 0) sum_slots(0, vprev);
-            const uint32_t dst = mapa_shared(smem_u32(slots + ((size_t)(sub * cs + rank) * M) * GV_TILE_N), 0);
-            #pragma unroll
-            for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) st_cluster_f32(dst + (uint32_t)(m * GV_TILE_N + ecol) * 4u, v[i]); }
-            cluster_arrive();                                 // release
+            if (sub == 0) cluster_wait();                     // barrier #0 complete: the leader is running, its mbarriers are initialised
+            if (rank != 0) {
+                const uint32_t dst = mapa_shared(smem_u32(slots + ((size_t)(sub * cs + rank) * M) * GV_TILE_N), 0);
+                const uint32_t bar = mapa_shared(smem_u32(&red_bar[sub]), 0);
+                #pragma unroll
+                for (int i = 0; i < 4; i++) { const int m = em0 + 2 * i; if (m < M) st_async_f32(dst + (uint32_t)(m * GV_TILE_N + ecol) * 4u, v[i], bar); }
+            } else if (NSUB == 2) {
+                if (sub == 0) {
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) vprev[i] = v[i];
+                } else {
+                    mbar_wait(&red_bar[0], 0);                // the gate tile's partials arrived while the up tile was computed
+                    sum_slots(0, vprev);
+                }
+            }
         } else if (NSUB == 2 && sub == 0) {
             #pragma unroll
             for (int i = 0; i < 4; i++) vprev[i] = v[i];
         }
     }
     if (cs > 1) {
-        cluster_wait();                                       // acquire: all partials of the last sub-tile are in our smem
-        if (rank != 0) return;
+        if (rank != 0) return;                                // nothing of this CTA is read by anyone: no closing cluster barrier
+        mbar_wait(&red_bar[NSUB - 1], 0);
         sum_slots(NSUB - 1, v);
     }
 
