@@ -398,6 +398,11 @@ def main():
                "sample": f"oracle CPU port (dequant + fp32 GEMV, OpenMP) of one decoder layer's 7 q4 matmuls, M=1, x{shape.layers}; {n} reps"}
 
     best_ms = time_ctx(4) if world == 1 else None
+    tp_timeouts = None
+    if fused_ar:
+        tt = torch.tensor([_ce.exllama_ext.tp_status(dev.index)], device=dev, dtype=torch.int64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        tp_timeouts = int(tt.item())          # flag waits of the fused all-reduce that gave up, over all ranks: must be 0
 
     if rank == 0:
         line = {
@@ -418,6 +423,7 @@ def main():
             "kernels": kern_rows,
             "cpu_baseline": cpu,
             "prefill": prefill,
+            "tp_allreduce_timeouts": tp_timeouts,
             "decode_torch_attention": {"value": round(1000.0 / torch_attn_ms, 2), "unit": "tok/s", "mode": "cuda graph",
                                        "note": "same step with the reference's torch attention ops instead of decode_attn"} if torch_attn_ms else None,
             "decode_best_ctx4": {"value": round(1000.0 / best_ms, 2), "unit": "tok/s", "mode": "eager"} if best_ms else None,

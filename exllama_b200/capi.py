@@ -39,6 +39,7 @@ SIGNATURES = {
                     [vp, vp, i32] * 3 + [vp, i32, vp]),
     "exl_q4_attn_2": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     "exl_q4_mlp": (i32, [vp, vp, f32, vp, vp, vp, i32, i32] + [vp, vp, i32] * 3 + [vp, i32, vp]),
+    "exl_tp_status": (i32, [i32, C.POINTER(C.c_uint)]),
     "exl_decode_attn": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "exl_q4_attn_2_tp": (i32, [vp, vp, vp, i32, i32, vp]),
     "exl_tp_workspace_alloc": (i32, [i32, C.POINTER(vp), vp]),

@@ -546,6 +546,16 @@ int exl_tp_init(int device, int rank, int world, void* const* workspace_ptrs)
     return EXL_OK;
 }
 
+int exl_tp_status(int device, unsigned* timeouts)
+{
+    ExlDevice* ds = exl_device_state(device);
+    if (!ds) return EXL_ERR_CUDA;
+    if (!ds->tp_local) return exl_set_err(EXL_ERR_STATE, "tp_status: no workspace on device %d", device);
+    DeviceGuard guard(device);
+    EXL_CUDA_TRY(cudaMemcpy(timeouts, ds->tp_local + TP_DATA_BYTES + TP_FLAG_BYTES + 2 * sizeof(unsigned), sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return EXL_OK;
+}
+
 int exl_q4_attn_2_tp(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, int add_residual, void* stream)
 {
     if (!o_proj) return exl_set_err(EXL_ERR_STATE, "q4_attn_2_tp: NULL handle");

@@ -72,7 +72,8 @@ constexpr int TP_MAX_RANKS = 8;
 constexpr int TP_MAX_TILES = 256;
 constexpr size_t TP_DATA_BYTES = (size_t)2 * TP_MAX_RANKS * TP_MAX_TILES * 8 * 128 * sizeof(float);
 constexpr size_t TP_FLAG_BYTES = (size_t)2 * TP_MAX_RANKS * TP_MAX_TILES * sizeof(unsigned);
-constexpr size_t TP_WS_BYTES = TP_DATA_BYTES + TP_FLAG_BYTES + 256;
+constexpr size_t TP_WS_BYTES = TP_DATA_BYTES + TP_FLAG_BYTES + 256;       // + control words {epoch, done, timeouts}
+constexpr unsigned TP_SPIN_LIMIT = 1u << 23;                                // polls of the own flag word (~ seconds) before giving up
 
 extern ExlTuning g_tuning;
 extern std::atomic<int64_t> g_launches;

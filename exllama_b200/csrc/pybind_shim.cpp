@@ -326,6 +326,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("q4_attn_2_tp", &q4_attn_2_tp, "q4_attn_2_tp");
     m.def("q4_mlp_tp", &q4_mlp_tp, "q4_mlp_tp");
     m.def("decode_attn", &decode_attn, "decode_attn");
+    m.def("tp_status", [](int device) { unsigned t = 0; EXL_CALL(exl_tp_status(device, &t)); return (int)t; }, "tp_status");
     m.def("tp_workspace_alloc", &tp_workspace_alloc, "tp_workspace_alloc");
     m.def("tp_workspace_open", &tp_workspace_open, "tp_workspace_open");
     m.def("tp_init", &tp_init, "tp_init");

@@ -766,7 +766,12 @@ __global__ void __launch_bounds__(THREADS, GV_MINB) q4_gemv_kernel(const __grid_
                 unsigned* pf = reinterpret_cast<unsigned*>(a.tp_peers[tid] + TP_DATA_BYTES) + ((size_t)par * TP_MAX_RANKS + R) * TP_MAX_TILES + tile_id;
                 st_release_sys_u32(pf, epoch + 1u);
                 const unsigned* mf = reinterpret_cast<const unsigned*>(a.tp_peers[R] + TP_DATA_BYTES) + ((size_t)par * TP_MAX_RANKS + tid) * TP_MAX_TILES + tile_id;
-                while (ld_acquire_sys_u32(mf) != epoch + 1u) { }
+                // bounded spin: a peer that never shows up (crashed rank, mismatched launch sequence) must not hang the GPU;
+                // the miss is counted in ctl[2] (exl_tp_status) and the result of this launch is then undefined
+                unsigned spins = 0;
+                while (ld_acquire_sys_u32(mf) != epoch + 1u) {
+                    if (++spins > TP_SPIN_LIMIT) { atomicAdd(ctl + 2, 1u); break; }
+                }
             }
             consumer_sync();
             float tot[4] = {0.f, 0.f, 0.f, 0.f};

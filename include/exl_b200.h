@@ -173,6 +173,9 @@ int exl_q4_mlp_tp(void* x, const void* rms_norm_weight, float epsilon,
 int exl_tp_workspace_alloc(int device, void** local_ptr, void* ipc_handle_64bytes);
 int exl_tp_workspace_open(int device, const void* ipc_handle_64bytes, void** peer_ptr);
 int exl_tp_init(int device, int rank, int world, void* const* workspace_ptrs /* [world], own entry = local_ptr */);
+
+/* Number of flag waits of the fused all-reduce that gave up (bounded spin) since the workspace was allocated; 0 = healthy. */
+int exl_tp_status(int device, unsigned* timeouts);
 /* x += all_reduce_sum(attn_output_local . o_proj_rowshard)            (every rank ends with the same x) */
 int exl_q4_attn_2_ar(void* x, const void* attn_output, const exl_q4_matrix* o_proj, int height, void* stream);
 /* x += all_reduce_sum(down_rowshard(silu(gate(n)) * up(n))),  n = rms_norm(x)   */

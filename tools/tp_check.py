@@ -84,8 +84,9 @@ if os.environ.get("EXL_TP_FUSED", "1") == "1":
     graph_ok = torch.equal(fy.cpu(), torch.from_numpy(f2))
     # NCCL sums fp16 partials, the fused kernel sums fp32 partials: allow two fp16 ulps of the largest value
     m1 = float(np.abs(x1.astype(np.float64)).max()); m2 = float(np.abs(x2.astype(np.float64)).max())
-    fused_ok = bool(d1 <= 2e-3 * m1 and d2 <= 2e-3 * m2 and same and loop_ok and graph_ok)
-    print(f"rank {rank}: fused all-reduce: |fused - nccl| {d1:.3e} / {d2:.3e}, identical on all ranks {same}, 60 launches {loop_ok}, graph x30 {graph_ok}", flush=True)
+    timeouts = ext.tp_status(torch.cuda.current_device())
+    fused_ok = bool(d1 <= 2e-3 * m1 and d2 <= 2e-3 * m2 and same and loop_ok and graph_ok and timeouts == 0)
+    print(f"rank {rank}: fused all-reduce: |fused - nccl| {d1:.3e} / {d2:.3e}, identical on all ranks {same}, 60 launches {loop_ok}, graph x30 {graph_ok}, flag timeouts {timeouts}", flush=True)
 
 if rank == 0:
     r1 = O.q4_matmul_f64(attn, *full["o"], acc_in=x)
