@@ -1,4 +1,7 @@
-set -x
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 300 python tools/kbench.py --shapes 7b 33b --reps 5 2>&1 | cut -c1-110
-timeout 600 python bench.py --no-prefill --no-cpu-baseline > gpurun_out/bench_r1d.json 2> gpurun_out/bench_r1d.err; head -c 300 gpurun_out/bench_r1d.json; tail -3 gpurun_out/bench_r1d.err
+for v in "EXL_GV_CAP=1" "EXL_GV_CAP=1 EXL_GV_PDL=0"; do
+  echo "== $v"
+  env $v timeout 200 python bench.py --no-prefill --no-cpu-baseline --steps 32 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], [(k['kernel'][:8],k['us']) for k in d['kernels']])"
+done
