@@ -92,8 +92,11 @@ class DecodeStack:
         self.n_layers = layers if layers is not None else shape.layers
         self.tp_rank, self.tp_size, self.tp_group = tp_rank, tp_size, tp_group
         self.fused_decode_attn = True          # csrc/decode_attn.cu instead of the torch ops of model.py:395-409
-        if act_order and tp_size > 1:
-            raise NotImplementedError("tensor parallel + act-order needs the x_map exchange (SURVEY.md 8e hazard 1)")
+        # act-order + tensor parallel (tp.py "act-order checkpoints"): row-parallel shards are cut on group ranges; down's
+        # input is local (gate/up column-gathered to match), o_proj's input is the all-gathered attention output indexed
+        # by the shard's rows.  The synthetic stack draws every rank's shard directly (a valid local act-order matrix) and
+        # a random row set for o_proj, so the work and the exchange are those of a real sharded checkpoint.
+        self.o_rows = None
         plan = tpmod.plan_shards(shape.hidden, shape.inter, shape.heads, shape.head_dim, groupsize, tp_size)
         self.plan = plan
         h = shape.hidden
@@ -115,6 +118,10 @@ class DecodeStack:
                 L.ln1 = (1 + 0.05 * torch.randn(h, device=self.device, generator=gen)).half()
                 L.ln2 = (1 + 0.05 * torch.randn(h, device=self.device, generator=gen)).half()
                 self.layers.append(L)
+            if act_order and tp_size > 1:
+                g0 = torch.Generator(device="cpu"); g0.manual_seed(seed * 7919 + 13)            # same on every rank
+                perm = torch.randperm(h, generator=g0)
+                self.o_rows = perm[tp_rank * hq:(tp_rank + 1) * hq].sort().values.to(self.device)
             self.norm = (1 + 0.05 * torch.randn(h, device=self.device, generator=gen)).half()
             self.lm_head = (torch.randn((shape.vocab, h), device=self.device, generator=gen) * 0.02).half() if with_head else None
             # sin/cos tables as model.py:864-877
@@ -173,12 +180,20 @@ class DecodeStack:
                 ext.q4_attn_2(x2, attn.view(-1, hq), L.o.q4, none, none, none)
                 ext.q4_mlp(x2, L.ln2, s.eps, L.gate.q4, L.up.q4, L.down.q4, none, none, none, none, none, none, none)
             else:
-                tpmod.row_parallel_residual(ext, x2, attn.view(-1, hq), L.o.q4, self.tp_rank, self.tp_group)
+                tpmod.row_parallel_residual(ext, x2, self._o_input(attn.view(-1, hq)), L.o.q4, self.tp_rank, self.tp_group)
                 tpmod.mlp_tp(ext, cuda_ext, x2, L, s.eps, self.tp_rank, self.tp_group)
         if self.lm_head is None:
             return hidden
         hn = cuda_ext.ext_rms_norm(hidden, self.norm, s.eps)
         return torch.matmul(hn.view(-1, s.hidden), self.lm_head.t()).float()
+
+    def _o_input(self, attn_local):
+        """o_proj input of this rank: its own heads' output, or -- act-order + TP -- the rows of its group range out of the
+        all-gathered attention output (the one extra exchange act-order costs, SURVEY.md 8e hazard 1)."""
+        if self.o_rows is None:
+            return attn_local
+        full = tpmod.all_gather_columns(attn_local, [attn_local.shape[1]] * self.tp_size, self.tp_group)
+        return full.index_select(1, self.o_rows)
 
     # ---- prefill: unfused path (model.py:532-550) --------------------------------------------------------------
     def prefill(self, hidden, past_len=0, last_only=True):
@@ -203,7 +218,7 @@ class DecodeStack:
                 raise NotImplementedError("chunked prefill with past is outside the benchmarked path")
             attn = torch.nn.functional.scaled_dot_product_attention(q, keys, values, attn_mask=None, is_causal=True)
             attn = attn.transpose(1, 2).reshape(bsz, q_len, hq)
-            o = L.o.forward(attn)
+            o = L.o.forward(self._o_input(attn.view(-1, hq)).view(bsz, q_len, hq))
             if self.tp_size > 1:
                 tpmod.all_reduce(o, self.tp_group)
             hidden = residual + o

@@ -62,6 +62,94 @@ def shard_q4_rows(qweight, qzeros, scales, k0, k1, groupsize):
     return qweight[k0 // 8:k1 // 8], qzeros[k0 // groupsize:k1 // groupsize], scales[k0 // groupsize:k1 // groupsize]
 
 
+# ---- act-order (g_idx) checkpoints ---------------------------------------------------------------------------------
+# Column-parallel projections need nothing special: every rank holds all K rows, hence the whole g_idx.
+# Row-parallel projections cannot be cut on contiguous k: the rows of one quantisation group are scattered over k
+# (SURVEY.md 8e hazard 1).  They are cut on GROUP ranges instead -- rank r owns the rows whose group lies in
+# [g0, g1) -- which keeps every local group complete (exactly `groupsize` rows), so the shard is itself a valid
+# act-order GPTQ matrix with local g_idx = g_idx[rows] - g0 that make_q4 / the kernels take unchanged.  The rank's
+# input is then x[:, rows]:
+#   * down_proj: gate/up are column-GATHERED with the same `rows`, so each rank's silu(gate)*up already is x[:, rows];
+#   * o_proj:    `rows` spans all heads, so the local heads' attention output is all-gathered once and indexed.
+
+def unpack_rows(qweight):
+    """int32 [K/8, N] (8 nibbles along K per word, exllama_ext.cpp:166-176) -> uint8 [K, N]."""
+    qw = np.ascontiguousarray(qweight).view(np.uint32)
+    out = np.empty((qw.shape[0], 8, qw.shape[1]), dtype=np.uint8)
+    for i in range(8):
+        out[:, i, :] = (qw >> np.uint32(4 * i)) & np.uint32(15)
+    return out.reshape(qw.shape[0] * 8, qw.shape[1])
+
+
+def pack_rows(w):
+    """uint8 [K, N] -> int32 [K/8, N]."""
+    K, N = w.shape
+    assert K % 8 == 0
+    w3 = w.reshape(K // 8, 8, N).astype(np.uint32)
+    out = np.zeros((K // 8, N), dtype=np.uint32)
+    for i in range(8):
+        out |= w3[:, i, :] << np.uint32(4 * i)
+    return out.view(np.int32)
+
+
+def unpack_cols(qzeros):
+    """int32 [G, N/8] (8 nibbles along N per word) -> uint8 [G, N]."""
+    qz = np.ascontiguousarray(qzeros).view(np.uint32)
+    out = np.empty((qz.shape[0], qz.shape[1], 8), dtype=np.uint8)
+    for i in range(8):
+        out[:, :, i] = (qz >> np.uint32(4 * i)) & np.uint32(15)
+    return out.reshape(qz.shape[0], qz.shape[1] * 8)
+
+
+def pack_cols(z):
+    G, N = z.shape
+    assert N % 8 == 0
+    z3 = z.reshape(G, N // 8, 8).astype(np.uint32)
+    out = np.zeros((G, N // 8), dtype=np.uint32)
+    for i in range(8):
+        out |= z3[:, :, i] << np.uint32(4 * i)
+    return out.view(np.int32)
+
+
+def plan_group_ranges(groups, tp):
+    """[(g0, g1)] per rank: whole quantisation groups, floor/ceil when they do not divide."""
+    _, offs = _split_even(groups, tp)
+    return [(offs[r], offs[r + 1]) for r in range(tp)]
+
+
+def act_order_row_shard(qweight, qzeros, scales, g_idx, g0, g1, groupsize):
+    """Row shard of an act-order GPTQ matrix on the group range [g0, g1) (numpy, host side, load time).
+    Returns (qweight_local, qzeros_local, scales_local, g_idx_local, rows): rows = ascending original k of the shard;
+    the shard multiplies x[:, rows]."""
+    g_idx = np.asarray(g_idx)
+    rows = np.nonzero((g_idx >= g0) & (g_idx < g1))[0]
+    assert rows.size == (g1 - g0) * groupsize, "every quantisation group must have exactly `groupsize` rows"
+    qw = pack_rows(unpack_rows(qweight)[rows])
+    return (qw, np.ascontiguousarray(qzeros[g0:g1]), np.ascontiguousarray(scales[g0:g1]),
+            (g_idx[rows] - g0).astype(np.int32), rows)
+
+
+def gather_q4_columns(qweight, qzeros, scales, cols):
+    """Column gather (arbitrary column list, len % 8 == 0) of a GPTQ tensor set; g_idx (a K property) is unaffected."""
+    cols = np.asarray(cols)
+    assert cols.size % 8 == 0
+    return (np.ascontiguousarray(np.asarray(qweight)[:, cols]), pack_cols(unpack_cols(qzeros)[:, cols]),
+            np.ascontiguousarray(np.asarray(scales)[:, cols]))
+
+
+def all_gather_columns(t_local, sizes, group=None):
+    """[M, n_local] per rank -> [M, sum(sizes)] on every rank (the o_proj input exchange of the act-order case)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if len(set(sizes)) == 1:
+        parts = [torch.empty_like(t_local) for _ in range(world)]
+    else:
+        parts = [t_local.new_empty((t_local.shape[0], n)) for n in sizes]
+    dist.all_gather(parts, t_local.contiguous(), group=group)
+    return torch.cat(parts, dim=1)
+
+
 def all_reduce(t, group=None):
     import torch.distributed as dist
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
