@@ -124,6 +124,10 @@ def cpu_baseline_sample(shape, gs, seconds_budget=12.0):
     return ms_layer, O.num_threads(), n
 
 
+def workload_name(shape, gs, ctx, seq):
+    return f"{shape.name}-gptq4-g{gs}-noact decode token at ctx {ctx} of seq {seq}"
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the path (the reference has no CPU implementation)."""
     from exllama_b200.stack import SHAPES
@@ -145,7 +149,8 @@ def run_reference(args):
         "impl": "reference", "metric": "decode tok/s Llama-7B 4b GPTQ g128 (q4 hot path)", "value": round(val, 4), "unit": "tok/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_tok, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{shape.name}-gptq4-g{args.groupsize}-noact decode token (CPU restatement, bounded sample)"},
+        "config": {"workload": workload_name(shape, args.groupsize, args.ctx, args.seq),
+                   "detail": "CPU restatement of the q4 matmuls of the step, bounded sample (the reference has no CPU path)"},
         "cpu_baseline": {"value": round(val, 4), "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -412,8 +417,9 @@ def main():
             "value": round(value, 2), "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"{shape.name}-gptq4-g{gs}-noact decode token at ctx {past} of seq {args.seq}: {shape.layers} layers x "
-                                   "(q4_attn, " + ("decode_attn kernel" if stack.fused_decode_attn else "torch attention ops") + " over the KV cache, q4_attn_2, q4_mlp) + final norm + fp16 lm_head",
+            "config": {"workload": workload_name(shape, gs, past, args.seq),
+                       "detail": f"{shape.layers} layers x (q4_attn, " + ("decode_attn kernel" if stack.fused_decode_attn else "torch attention ops") +
+                                 " over the KV cache, q4_attn_2, q4_mlp) + final norm + fp16 lm_head",
                        "parallelism": f"tp{world}", "cuda_graph": graph is not None, "allreduce": ("fused GEMV epilogue over NVLink peer memory" if fused_ar else ("nccl" if world > 1 else None)),
                        "l2": "weights (3.6 GB/token) >> L2, every step streams them from HBM"},
             "e2e": {"value": round(1000.0 / e2e_ms, 2), "unit": "tok/s", "h2d_bytes_per_step": host_in.numel() * 2,

@@ -127,6 +127,16 @@ int exl_cleanup(void)
         ExlDevice* ds = &g_devices[i];
         ds->temp_state = nullptr; ds->temp_mlp = nullptr; ds->temp_zeros_float = nullptr; ds->temp_dq = nullptr;
         ds->temp_state_numel = ds->temp_mlp_numel = ds->temp_dq_numel = 0; ds->max_zeros_float = 0;
+        if (ds->tp_local) {
+            // tensor-parallel workspace: unmap the peers' buffers, free our own (peers must have stopped launching)
+            DeviceGuard guard(i);
+            for (int p = 0; p < TP_MAX_RANKS; p++) {
+                if (ds->tp_peers[p] && ds->tp_peers[p] != ds->tp_local) cudaIpcCloseMemHandle(ds->tp_peers[p]);
+                ds->tp_peers[p] = nullptr;
+            }
+            cudaFree(ds->tp_local);
+            ds->tp_local = nullptr; ds->tp_rank = 0; ds->tp_world = 1;
+        }
     }
     return EXL_OK;
 }
