@@ -24,7 +24,8 @@
 //    (the reference accumulates in fp16, matrix.cuh:87-133).
 //  * split-K without global memory: one thread-block CLUSTER owns one 128-column tile; its CS CTAs take contiguous
 //    K slices and the leader sums the CS partials out of its own shared memory, where the peers deposited them
-//    through DSMEM (st.shared::cluster) before a cluster barrier.  Fixed summation order => deterministic; no fp16
+//    through DSMEM with st.async (the stores complete transaction bytes on an mbarrier of the leader, so no
+//    cluster-scope fence is needed and the peers exit right away).  Fixed summation order => deterministic; no fp16
 //    atomics (the reference: q4_matmul.cu:203-211) and no L2 round trips on the critical path.
 //  * programmatic dependent launch: weights do not depend on the previous kernel, so the producer warp fills the
 //    whole TMA ring BEFORE the consumers' griddepcontrol.wait, and launch_dependents is signalled as soon as the
