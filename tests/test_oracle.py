@@ -135,3 +135,29 @@ def test_decode_attn_against_torch_fixture(oracle):
         scale = max(1.0, np.abs(exact).max())
         assert np.abs(r16 - g[f"f16_{i}"]).max() <= 3e-3 * scale
         assert np.abs(r16 - exact).max() <= 5e-3 * scale
+
+
+@pytest.mark.parametrize("K,N,gs", [(1024, 64, 128), (2048, 32, 32), (512, 96, 512)])
+def test_int16_group_quantisation_of_x_error_bound(oracle, K, N, gs):
+    """The decode kernel's arithmetic restated in numpy (q4_gemv.cu: x carried per quantisation group as a 16-bit integer
+    with its own scale, exact integer dot products against the raw nibbles, zero point folded in as zp * sum(x_q), groups
+    combined in fp32 with the fp16 scales): the claimed bound -- within 1e-4 of the output rms of the exact result for
+    groupsize <= 128 -- holds on the synthetic tensors the parity tests use."""
+    qw, qz, sc, _ = oracle.synth_q4(K, N, gs, seed=K + N)
+    x = oracle.synth_x(3, K, seed=5)
+    exact = oracle.q4_matmul_f64(x, qw, qz, sc)
+    q = ((qw.view(np.uint32)[:, None, :] >> (4 * np.arange(8, dtype=np.uint32))[None, :, None]) & 15).reshape(K, N).astype(np.int64)
+    z = ((qz.view(np.uint32)[:, :, None] >> (4 * np.arange(8, dtype=np.uint32))[None, None, :]) & 15).reshape(K // gs, N).astype(np.int64) + 1
+    out = np.zeros((3, N), dtype=np.float32)
+    for g in range(K // gs):
+        xs = x[:, g * gs:(g + 1) * gs].astype(np.float32)
+        mx = np.abs(xs).max(axis=1, keepdims=True)
+        inv = np.where(mx > 0, np.float32(32767.0) / mx, 0).astype(np.float32)
+        xq = np.rint(xs * inv).astype(np.int64)                              # |x_q| <= 32767
+        dot = xq @ q[g * gs:(g + 1) * gs] - xq.sum(axis=1, keepdims=True) * z[g][None, :]       # exact integers
+        assert np.abs(dot).max() < 2 ** 31
+        sx = (mx * np.float32(1.0 / 32767.0)).astype(np.float32)
+        out += (sc[g].astype(np.float32)[None, :] * sx) * dot.astype(np.float32)
+    rms = np.sqrt(np.mean(exact ** 2))
+    # below the fp16 rounding of the result (2^-11) in every case; < 1e-4 for the usual group sizes
+    assert np.abs(out - exact).max() <= (1e-4 if gs <= 128 else 4e-4) * rms
