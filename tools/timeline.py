@@ -1,5 +1,7 @@
 """Kernel timeline of one graph-replayed decode step (CUPTI through torch.profiler): start, duration and the gap to the
-previous kernel for every launch of a few layers, plus per-kernel totals.  Diagnostic only (CUPTI adds overhead)."""
+previous kernel for every launch of a few layers, plus per-kernel totals.  Diagnostic only (CUPTI adds overhead).
+Caution: the second time this ran on the GPU box it produced no output for 300 s and was killed by its timeout (cause not
+established; kineto + graph-launched cluster/PDL kernels is an unusual mix) -- always run it under `timeout`."""
 import json
 import os
 import sys
