@@ -52,17 +52,6 @@ ExlDevice* exl_device_state(int device)
     DeviceGuard guard(device);
     ds->device = device;
     ds->num_sms = prop.multiProcessorCount;
-    const size_t partial_bytes = (size_t)GV_MAX_CTAS * 2 * GV_MAXM * GV_TILE_N * sizeof(float);
-    const size_t pair_bytes = (size_t)GV_MAX_PAIRS * 2 * GV_MAXM * GV_TILE_N * sizeof(float);
-    if (cudaMalloc(&ds->gemv_partials, partial_bytes) != cudaSuccess ||
-        cudaMalloc(&ds->gemv_counters, GV_MAX_TILES * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&ds->gemv_pair_stage, pair_bytes) != cudaSuccess ||
-        cudaMalloc(&ds->gemv_pair_counters, GV_MAX_PAIRS * sizeof(unsigned)) != cudaSuccess) {
-        exl_set_err(EXL_ERR_CUDA, "workspace allocation failed on device %d", device);
-        return nullptr;
-    }
-    cudaMemset(ds->gemv_counters, 0, GV_MAX_TILES * sizeof(unsigned));
-    cudaMemset(ds->gemv_pair_counters, 0, GV_MAX_PAIRS * sizeof(unsigned));
     if (cublasCreate(&ds->blas) != CUBLAS_STATUS_SUCCESS) { exl_set_err(EXL_ERR_CUDA, "cublasCreate failed"); return nullptr; }
     cudaDeviceSynchronize();
     ds->init = true;

@@ -53,10 +53,6 @@ struct ExlDevice
     float* temp_zeros_float = nullptr; int max_zeros_float = 0;
     half* temp_dq = nullptr;     int64_t temp_dq_numel = 0;
     // owned
-    float* gemv_partials = nullptr;     // [GV_MAX_CTAS * 2][GV_MAXM][GV_TILE_N]
-    unsigned* gemv_counters = nullptr;  // [GV_MAX_TILES]
-    float* gemv_pair_stage = nullptr;   // [GV_MAX_PAIRS][2][GV_MAXM][GV_TILE_N]
-    unsigned* gemv_pair_counters = nullptr;  // [GV_MAX_PAIRS]
     half* own_norm = nullptr;  int64_t own_norm_numel = 0;   // scratch for fused ops when temp_state is absent
     cublasHandle_t blas = nullptr;
     int gemv_ctas_per_sm = 0;
@@ -152,6 +148,3 @@ int exl_half_matmul_custom_launch(const half* x, const half* w, half* out, int M
 
 constexpr int GV_TILE_N = 128;
 constexpr int GV_MAXM = 8;
-constexpr int GV_MAX_CTAS = 148 * 8;
-constexpr int GV_MAX_TILES = 4096;
-constexpr int GV_MAX_PAIRS = 512;
