@@ -195,3 +195,20 @@ def test_tp2_act_order_matches_single_rank_gloo(oracle):
     g = O.ref64_with_act_order(x1_tp, *cp(gate_full)).astype(np.float16); u = O.ref64_with_act_order(x1_tp, *cp(up_full)).astype(np.float16)
     x2 = O.ref64_with_act_order(O.silu_mul(g, u), *cp(down_full), acc_in=x1_tp)
     np.testing.assert_allclose(x2_tp, x2, rtol=1e-9, atol=1e-9 * np.abs(x2).max())
+
+
+def test_plan_baseline_configs():
+    """Shard plans of the tensor-parallel BASELINE configs (33B g32 over 2 and 4 ranks, 65B g128 over 8): whole heads, whole
+    groups, kernel granularities (row shards % 32, column shards % 32), and the act-order group ranges tile the groups."""
+    from exllama_b200 import tp
+    for hidden, inter, heads, gs, worlds in ((6656, 17920, 52, 32, (2, 4)), (8192, 22016, 64, 128, (2, 4, 8)), (4096, 11008, 32, 128, (2, 4, 8))):
+        for w in worlds:
+            p = tp.plan_shards(hidden, inter, heads, 128, gs, w)
+            assert sum(p.heads) == heads and p.head_cols[-1][1] == hidden and p.inter_cols[-1][1] == inter
+            for (a, b) in p.head_cols + p.inter_cols:
+                assert a % gs == 0 and b % gs == 0 and (b - a) % 32 == 0 and b > a
+            for total in (hidden // gs, inter // gs):
+                r = tp.plan_group_ranges(total, w)
+                assert r[0][0] == 0 and r[-1][1] == total and all(x[1] == y[0] for x, y in zip(r, r[1:]))
+                assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+                assert all(((b - a) * gs) % 32 == 0 for a, b in r)
