@@ -59,13 +59,17 @@ ExlDevice* exl_device_state(int device)
 }
 
 // library-owned scratch for callers that never called prepare_buffers (lazy; not CUDA-graph safe on first use)
-static int ensure_own_scratch(ExlDevice* ds, int64_t numel)
+int exl_own_scratch(ExlDevice* ds, int role, int64_t numel, half** out)
 {
-    if (ds->own_norm_numel >= numel) return EXL_OK;
-    if (ds->own_norm) cudaFree(ds->own_norm);
-    ds->own_norm = nullptr; ds->own_norm_numel = 0;
-    EXL_CUDA_TRY(cudaMalloc(&ds->own_norm, (size_t)numel * sizeof(half)));
-    ds->own_norm_numel = numel;
+    if (ds->own_numel[role] < numel) {
+        // growing = synchronize + cudaFree + cudaMalloc; during stream capture the synchronize fails and the error is returned
+        // (call the op once eagerly, or prepare_buffers, before capturing a graph)
+        if (ds->own[role]) { EXL_CUDA_TRY(cudaDeviceSynchronize()); cudaFree(ds->own[role]); }
+        ds->own[role] = nullptr; ds->own_numel[role] = 0;
+        EXL_CUDA_TRY(cudaMalloc(&ds->own[role], (size_t)numel * sizeof(half)));
+        ds->own_numel[role] = numel;
+    }
+    *out = ds->own[role];
     return EXL_OK;
 }
 
@@ -161,8 +165,9 @@ int exl_make_q4(void* qweight, void* qzeros, void* scales, const int32_t* g_idx_
             cudaMalloc(&tmp, (size_t)(K / 8) * N * sizeof(uint32_t)) != cudaSuccess) {
             delete m; return exl_set_err(EXL_ERR_CUDA, "make_q4: cudaMalloc failed");
         }
-        cudaMemcpyAsync(m->x_map, x_map.data(), (size_t)K * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
-        int rc = exl_make_sequential_launch(m->qweight, tmp, m->x_map, K, N, stream);
+        cudaError_t ec = cudaMemcpyAsync(m->x_map, x_map.data(), (size_t)K * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+        int rc = ec == cudaSuccess ? exl_make_sequential_launch(m->qweight, tmp, m->x_map, K, N, stream)
+                                   : exl_set_err(EXL_ERR_CUDA, "make_q4: x_map upload failed: %s", cudaGetErrorString(ec));
         cudaError_t e = cudaStreamSynchronize(stream);     // x_map (host vector) and tmp die here
         cudaFree(tmp);
         if (rc != EXL_OK || e != cudaSuccess) {
@@ -204,14 +209,8 @@ static int q4_matmul_recons_cublas(ExlDevice* ds, const half* x, int M, const ex
     half* xm = nullptr;
     const int64_t xm_numel = w->x_map ? (int64_t)M * w->K : 0;
     if (w->x_map && ds->temp_state_numel >= xm_numel) xm = ds->temp_state;
-    int64_t need = (dq ? 0 : dq_numel) + ((w->x_map && !xm) ? xm_numel : 0);
-    if (need > 0) {
-        int rc = ensure_own_scratch(ds, need);
-        if (rc != EXL_OK) return rc;
-        half* p = ds->own_norm;
-        if (!dq) { dq = p; p += dq_numel; }
-        if (w->x_map && !xm) xm = p;
-    }
+    if (!dq) { int rc = exl_own_scratch(ds, SCR_DQ, dq_numel, &dq); if (rc != EXL_OK) return rc; }
+    if (w->x_map && !xm) { int rc = exl_own_scratch(ds, SCR_REMAP, xm_numel, &xm); if (rc != EXL_OK) return rc; }
     const half* xin = x;
     if (w->x_map) {
         int rc = exl_column_remap_launch(x, xm, M, w->K, w->x_map, stream);
@@ -368,17 +367,22 @@ int exl_q4_attn(void* x_, const void* rms_norm_weight, float epsilon, void* quer
     }
 
     // General path (LoRA, act-order with distinct x_maps, other head sizes): same sequence as q4_attn_cuda.
+    // The hidden width is the projections' K, not the caller's `dim` (= query_states.size(2), exllama_ext.cpp:470): under
+    // tensor parallelism the query width is hidden / tp while x, the norm and the q/k/v inputs are hidden wide.
+    const int hid = q_proj->K;
+    if (k_proj->K != hid || v_proj->K != hid) return exl_set_err(EXL_ERR_ARG, "q4_attn: q/k/v projections disagree on the input width");
+    (void)dim;
     half* temp_x;
-    if (ds->temp_state && ds->temp_state_numel >= 2 * (int64_t)rows * dim) temp_x = ds->temp_state + (size_t)rows * dim;
-    else { int rc = ensure_own_scratch(ds, (int64_t)rows * dim); if (rc != EXL_OK) return rc; temp_x = ds->own_norm; }
-    int rc = exl_rms_norm_launch(x, (const half*)rms_norm_weight, temp_x, epsilon, rows, dim, stream);
+    if (ds->temp_state && ds->temp_state_numel >= 2 * (int64_t)rows * hid) temp_x = ds->temp_state + (size_t)rows * hid;
+    else { int rc = exl_own_scratch(ds, SCR_NORM, (int64_t)rows * hid, &temp_x); if (rc != EXL_OK) return rc; }
+    int rc = exl_rms_norm_launch(x, (const half*)rms_norm_weight, temp_x, epsilon, rows, hid, stream);
     if (rc != EXL_OK) return rc;
     struct P { const exl_q4_matrix* w; half* out; const void* a; const void* b; int rank; };
     P proj[3] = {{q_proj, (half*)query_states, q_a, q_b, q_rank}, {k_proj, (half*)key_states, k_a, k_b, k_rank},
                  {v_proj, (half*)value_states, v_a, v_b, v_rank}};
     for (int i = 0; i < 3; i++) {
         if (proj[i].rank) {
-            rc = exl_half_matmul_cublas_launch(ds, temp_x, (const half*)proj[i].a, (half*)lora_temp, rows, dim, proj[i].rank, false, stream);
+            rc = exl_half_matmul_cublas_launch(ds, temp_x, (const half*)proj[i].a, (half*)lora_temp, rows, hid, proj[i].rank, false, stream);
             if (rc != EXL_OK) return rc;
             rc = exl_half_matmul_cublas_launch(ds, (const half*)lora_temp, (const half*)proj[i].b, proj[i].out, rows, proj[i].rank, proj[i].w->N, false, stream);
             if (rc != EXL_OK) return rc;
@@ -430,10 +434,7 @@ static int q4_mlp_impl(void* x_, const void* rms_norm_weight, float epsilon, con
     const int64_t mlp_numel = 2 * (int64_t)height * inter;
     const bool have_norm = ds->temp_state && ds->temp_state_numel >= 2 * (int64_t)height * dim;
     if (ds->temp_mlp && ds->temp_mlp_numel >= mlp_numel) temp_mlp = ds->temp_mlp;
-    int64_t own_need = (temp_mlp ? 0 : mlp_numel) + (have_norm ? 0 : (int64_t)height * dim);
-    half* own = nullptr;
-    if (own_need) { int rc = ensure_own_scratch(ds, own_need); if (rc != EXL_OK) return rc; own = ds->own_norm; }
-    if (!temp_mlp) { temp_mlp = own; own += mlp_numel; }
+    if (!temp_mlp) { int rc = exl_own_scratch(ds, SCR_MLP, mlp_numel, &temp_mlp); if (rc != EXL_OK) return rc; }
 
     if (!lora && height <= GV_MAXM && gate->x_map == up->x_map && gate->N == up->N && gate->groups == up->groups) {
         // two launches instead of six (q4_mlp.cu:118-197): [norm -> gate,up -> silu*mul], [down += residual]
@@ -450,7 +451,8 @@ static int q4_mlp_impl(void* x_, const void* rms_norm_weight, float epsilon, con
     }
     if (all_reduce) return exl_set_err(EXL_ERR_ARG, "q4_mlp_ar: only the fused decode configuration (rows <= 8, no act-order mismatch) is supported");
 
-    half* temp_x = have_norm ? ds->temp_state + (size_t)height * dim : own;
+    half* temp_x = have_norm ? ds->temp_state + (size_t)height * dim : nullptr;
+    if (!temp_x) { int rc = exl_own_scratch(ds, SCR_NORM, (int64_t)height * dim, &temp_x); if (rc != EXL_OK) return rc; }
     half* t0 = temp_mlp; half* t1 = temp_mlp + (size_t)height * inter;
     int rc = exl_rms_norm_launch(x, (const half*)rms_norm_weight, temp_x, epsilon, height, dim, stream);
     if (rc != EXL_OK) return rc;

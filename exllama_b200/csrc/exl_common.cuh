@@ -53,7 +53,10 @@ struct ExlDevice
     float* temp_zeros_float = nullptr; int max_zeros_float = 0;
     half* temp_dq = nullptr;     int64_t temp_dq_numel = 0;
     // owned
-    half* own_norm = nullptr;  int64_t own_norm_numel = 0;   // scratch for fused ops when temp_state is absent
+    // library-owned scratch for callers that never called prepare_buffers (or passed buffers that are too small).
+    // One buffer PER ROLE: nested users (fused block -> q4_matmul -> act-order gather / reconstruct) never alias and a
+    // role is only ever grown by its own user, so no pointer handed out earlier in the same op can be freed under it.
+    half* own[4] = {nullptr, nullptr, nullptr, nullptr};  int64_t own_numel[4] = {0, 0, 0, 0};
     cublasHandle_t blas = nullptr;
     int gemv_ctas_per_sm = 0;
     // tensor-parallel one-shot all-reduce over NVLink peer memory (q4_gemv.cu, GV_EPI_ALLREDUCE)
@@ -74,6 +77,9 @@ constexpr unsigned TP_SPIN_LIMIT = 1u << 23;                                // p
 extern ExlTuning g_tuning;
 extern std::atomic<int64_t> g_launches;
 extern const char* g_last_q4_path;
+
+enum ExlScratchRole { SCR_NORM = 0, SCR_MLP = 1, SCR_DQ = 2, SCR_REMAP = 3 };
+int exl_own_scratch(ExlDevice* ds, int role, int64_t numel, half** out);   // grow-only, lazy; not CUDA-graph safe on first use
 
 int exl_set_err(int code, const char* fmt, ...);
 ExlDevice* exl_device_state(int device);          // lazily initialised; nullptr + error on failure

@@ -369,15 +369,7 @@ int exl_tc_gemm_launch(ExlDevice* ds, const half* x, int M, const exl_q4_matrix*
         const int64_t need = (int64_t)M * w->K;
         half* xm = nullptr;
         if (ds->temp_state && ds->temp_state_numel >= need) xm = ds->temp_state;
-        else {
-            if (ds->own_norm_numel < need) {
-                if (ds->own_norm) cudaFree(ds->own_norm);
-                ds->own_norm = nullptr; ds->own_norm_numel = 0;
-                EXL_CUDA_TRY(cudaMalloc(&ds->own_norm, (size_t)need * sizeof(half)));
-                ds->own_norm_numel = need;
-            }
-            xm = ds->own_norm;
-        }
+        else { int rc = exl_own_scratch(ds, SCR_REMAP, need, &xm); if (rc != EXL_OK) return rc; }
         int rc = exl_column_remap_launch(x, xm, M, w->K, w->x_map, stream);
         if (rc != EXL_OK) return rc;
         xin = xm;

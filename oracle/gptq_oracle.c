@@ -10,14 +10,18 @@
  * function below restates a CUDA kernel's arithmetic on the host and cites
  * the reference file:line it follows (paths relative to /root/reference/).
  *
- * Parity pinning:
- *   - orc_rep_penalty / orc_apply_rep_penalty are pinned bit-exactly against
- *     the reference's own rep_penalty.cpp compiled into oracle/_ref/
- *     (tests/test_oracle_pin.py) and against tests/golden/rep_penalty_*.npz.
- *   - the GPU ops are pinned against the reference's kernels compiled for
- *     sm_100a into oracle/_ref/libexllama_ref.so (run on the B200 box) and
- *     against golden vectors generated from that library
- *     (tests/golden/ref_gpu_*.npz, generated by oracle/gen_golden_gpu.py).
+ * Parity pinning (every file named here exists; the GPU pins run under `pytest -m gpu` on the B200 box):
+ *   - orc_rep_penalty / orc_apply_rep_penalty: bit-exact against the reference's own
+ *     rep_penalty.cpp compiled into oracle/_ref/librep_penalty_ref.so and against
+ *     tests/golden/rep_penalty_ref.npz (oracle/gen_golden_cpu.py)  -- tests/test_oracle.py.
+ *   - make_x_map / make_sequential / q4_matmul (decode + reconstruct flavours): against the
+ *     reference's kernels compiled for sm_100a into oracle/_ref/libexllama_ref.so
+ *     -- tests/test_gpu_q4_matmul.py::test_against_reference_*.
+ *   - rms_norm, rope, column_remap, half_matmul, update_cache and silu_mul (through the fused
+ *     q4_attn / q4_attn_2 / q4_mlp blocks): three-way against the same library
+ *     -- tests/test_gpu_ref_pin.py.
+ *   - orc_decode_attn: tests/golden/decode_attn_torch.npz (oracle/gen_golden_attn.py: the
+ *     reference's attention tensor program model.py:383-409 run with torch on the CPU).
  *
  * fp16 is handled with explicit bit conversions (round-to-nearest-even) so
  * the result does not depend on the host compiler's _Float16 support.
