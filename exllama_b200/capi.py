@@ -51,6 +51,10 @@ SIGNATURES = {
     "exl_rep_penalty": (i32, [i32, vp, vp, f32, i32, i32, i32]),
     "exl_apply_rep_penalty": (i32, [i32, vp, f32, i32, i32, i32, vp]),
     "exl_q4_matmul_host": (i32, [vp, i32, vp, vp, vp, vp, vp]),
+    "exl_decode_plan_create": (i32, [vp, C.POINTER(vp)]),
+    "exl_decode_plan_destroy": (i32, [vp]),
+    "exl_decode_plan_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
+    "exl_decode_step": (i32, [vp, vp, i32, vp, vp, vp]),
     "exl_launch_count": (i64, []),
     "exl_last_q4_path": (C.c_char_p, []),
 }
@@ -207,3 +211,54 @@ def launch_count() -> int:
 
 def last_q4_path() -> str:
     return lib().exl_last_q4_path().decode()
+
+
+class _DecodeDesc(C.Structure):
+    """struct exl_decode_desc (include/exl_b200.h)"""
+    _fields_ = [("n_layers", i32), ("num_heads", i32), ("head_dim", i32), ("max_seq_len", i32), ("vocab", i32), ("rms_eps", f32),
+                ("mats", C.POINTER(vp)), ("ln1", C.POINTER(vp)), ("ln2", C.POINTER(vp)), ("key_cache", C.POINTER(vp)),
+                ("value_cache", C.POINTER(vp)), ("sin", vp), ("cos", vp), ("final_norm", vp), ("lm_head", vp)]
+
+
+class DecodePlan:
+    """exl_decode_plan: the whole decode token as one persistent kernel (csrc/decode_step.cu).
+
+    handles: per layer the 7 Q4 handles (q, k, v, o, gate, up, down) as integers / c_void_p; every tensor passed here is
+    borrowed and must outlive the plan."""
+
+    def __init__(self, handles, ln1, ln2, key_cache, value_cache, sin, cos, num_heads, head_dim, max_seq_len, eps,
+                 final_norm=None, lm_head=None):
+        n = len(handles)
+        self._keep = (ln1, ln2, key_cache, value_cache, sin, cos, final_norm, lm_head)
+        flat = []
+        for hs in handles:
+            assert len(hs) == 7
+            flat += [h.value if isinstance(h, C.c_void_p) else int(h) for h in hs]
+        self._mats = (vp * (7 * n))(*flat)
+        arr = lambda ts: (vp * n)(*[t.data_ptr() for t in ts])
+        self._a = [arr(ln1), arr(ln2), arr(key_cache), arr(value_cache)]
+        d = _DecodeDesc()
+        d.n_layers, d.num_heads, d.head_dim, d.max_seq_len = n, num_heads, head_dim, max_seq_len
+        d.vocab = lm_head.shape[0] if lm_head is not None else 0
+        d.rms_eps = eps
+        d.mats = C.cast(self._mats, C.POINTER(vp))
+        d.ln1, d.ln2, d.key_cache, d.value_cache = (C.cast(x, C.POINTER(vp)) for x in self._a)
+        d.sin, d.cos = sin.data_ptr(), cos.data_ptr()
+        d.final_norm = final_norm.data_ptr() if final_norm is not None else None
+        d.lm_head = lm_head.data_ptr() if lm_head is not None else None
+        self.vocab = d.vocab
+        self.handle = vp()
+        check(lib().exl_decode_plan_create(C.byref(d), C.byref(self.handle)))
+
+    def info(self):
+        g, r, s, b = i32(), i32(), i64(), i64()
+        check(lib().exl_decode_plan_info(self.handle, C.byref(g), C.byref(r), C.byref(s), C.byref(b)))
+        return {"grid": g.value, "ring_stages": r.value, "smem_bytes": s.value, "barriers_per_step": b.value}
+
+    def step(self, x_in, past_len, x_out=None, logits=None):
+        check(lib().exl_decode_step(self.handle, _ptr(x_in), past_len, _ptr(x_out), _ptr(logits), _stream()))
+
+    def close(self):
+        if self.handle:
+            check(lib().exl_decode_plan_destroy(self.handle))
+            self.handle = None

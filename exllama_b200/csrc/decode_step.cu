@@ -1,0 +1,920 @@
+// decode_step.cu -- ONE persistent cooperative kernel for a whole decode token (bsz 1, q_len 1) on sm_100a.
+//
+// SURVEY.md 8f-4 ("host loop: a C++ decoder_layer op / whole-step capture") and the answer to VERDICT r1 item 1: the five
+// launches per layer (q4_attn, decode_attn, q4_attn_2, q4_mlp x2) were latency-bound -- launch + setup + x-dependent
+// prologue + split-K exchange around 1-9 us of streaming each.  Here the whole token is one launch:
+//
+//   for every layer:   QKV | ATT | O | GU | DOWN        (| = grid barrier)       then  final norm + fp16 lm_head
+//
+// replacing, per layer, rms_norm + 3 x q4_matmul + 2 x rope + update_cache (q4_attn.cu:74-165), the torch attention ops
+// (model.py:383-409), q4_matmul += residual (q4_attn.cu:206-228), rms_norm + 2 x q4_matmul + silu_mul + q4_matmul += residual
+// (q4_mlp.cu:100-199), and at the end model.py:1069-1077 (norm + lm_head).
+//
+// Structure (one CTA per SM, 16 consumer warps + 1 producer warp):
+//  * The PRODUCER warp walks a static schedule of 8 KB "stages" through a shared-memory ring with full/empty mbarriers and
+//    never waits for a grid barrier: weights (2-D TMA boxes of the packed qweight + 1-D bulk copies of the stage's scale /
+//    zero rows), KV-cache rows older than the current token (bulk copies) and lm_head rows do not depend on activations, so
+//    up to NST x 8 KB per SM (~24 MB chip-wide) of the NEXT phase is already in flight while the consumers are in a barrier
+//    or in a phase prologue.  HBM stays busy across phase and layer boundaries -- the thing separate launches could not do.
+//  * Work of a GEMV phase = (128-column tile) x (128-row K stage) units, flattened tile-major and cut into G equal contiguous
+//    ranges (G = grid size): every SM streams the same number of bytes whatever the matrix shapes (65B gate/up: 172 tiles on
+//    148 SMs is no longer a problem).  A warp accumulates its 32 columns over the stages it sees and, at a tile boundary,
+//    adds its fp32 partial into the phase's accumulator in L2 with red.global.add.v4.f32 -- the split-K reduction is the
+//    grid barrier that the data dependence needs anyway.
+//  * Inner product exactly as q4_gemv.cu (integer tensor cores, nibbles as the A operand straight from the ring, x carried
+//    per quantisation segment as a 16-bit integer), specialised for one token: the two byte planes of x ride in two of the
+//    eight B columns, so ONE mma.sync.m16n8k32.u8.s8 per 16 columns x 32 k does both planes.
+//  * The x-dependent part of a phase (residual add + RMS norm, rope + cache write, softmax-combine, silu*mul; then per-segment
+//    quantisation of the K range this CTA needs) runs after the barrier out of L2-resident fp32 accumulators; the residual
+//    stream itself lives in every CTA's shared memory in fp16, rounded where the reference rounds it.
+//  * ATT: (head, 16-position chunk) units, online softmax per warp in fp32 (as decode_attn.cu), partial (m, l, o) per CTA to
+//    L2, combined in the O prologue.  The newest K/V row never round-trips through HBM before it is used.
+//  * HEAD: lm_head [vocab, hidden] fp16 streamed as 8 KB stages, fp32 dot products, fp32 logits by red.global.add.
+//
+// Restrictions (checked on the host; anything else uses the per-op kernels): head_dim 128, kv_heads == heads, groupsize 32 * 2^n
+// (or one group), no act-order, widths multiples of 128.  Every wait is bounded by wall time and traps on expiry.
+#include "exl_common.cuh"
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int DS_CONSUMERS = 512;                // 16 consumer warps: 4 across the tile's columns x 4 across K stages
+constexpr int DS_THREADS = DS_CONSUMERS + 32;    // + producer warp
+constexpr int DS_NCW = DS_CONSUMERS / 32;
+constexpr int TILE = 128;                        // columns per tile == K rows per stage
+constexpr int W_BYTES = 8192;                    // packed weights of one unit: 16 k8-rows x 128 columns x 4 B
+constexpr int BOX_BYTES = 2048;                  // TMA box: 16 k8-rows x 32 columns, SWIZZLE_128B
+constexpr int META_SC = W_BYTES;                 // up to 4 group rows of 128 fp16 scales
+constexpr int META_ZQ = W_BYTES + 1024;          // up to 4 group rows of 128 zero nibbles
+constexpr int STAGE_STRIDE = W_BYTES + 2048;     // keeps every stage 1 KB aligned (swizzle atom)
+constexpr int PART_LD = 132;                     // attention partial: o[128], m, l, pad
+constexpr int MAX_LAYERS = 128;
+constexpr unsigned long long WAIT_NS = 4000000000ull;   // any single wait longer than this aborts the launch
+
+enum { PH_QKV = 0, PH_ATT = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_HEAD = 5 };
+
+struct alignas(64) LayerDesc
+{
+    CUtensorMap tm[7];                 // q k v o gate up down: qweight [K/8, N] int32, box 16 x 32, SWIZZLE_128B (exl_q4_matrix::tmap_w)
+    const uint32_t* qz[7];
+    const half* sc[7];
+    const half* ln1; const half* ln2;
+    half* kc; half* vc;                // [heads, max_seq, 128]
+};
+
+struct StepArgs
+{
+    const LayerDesc* layers; int n_layers;
+    int H, HQ, I;                      // hidden, attention width (heads * 128), intermediate width
+    int heads, max_seq, past_len;
+    int gshift;                        // log2(groupsize / 32); 30 = one group per matrix
+    int nst;                           // ring depth
+    int spt_max;                       // max K / 128 over the phases
+    float eps;
+    const half* x_in; half* x_out;     // [H] input hidden state; final hidden state (before the final norm), optional
+    const half* sin; const half* cos;  // [max_seq, 128]
+    const half* final_norm; const half* lm_head; float* logits; int vocab;     // optional head
+    float* acc_qkv; float* acc_o; float* acc_gu; float* acc_d;                 // fp32 phase accumulators in L2
+    float* att_part; int att_slots;    // [heads][att_slots][PART_LD]
+    unsigned* bar;                     // grid barrier {count, generation}
+};
+
+// ------------------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void mbar_init(void* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try(bar, parity)) return;
+    const unsigned long long t0 = gtime();
+    for (unsigned i = 1; !mbar_try(bar, parity); i++)
+        if ((i & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 r; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// u8 (weights, 0..15) x s8 (x planes) -> s32; first MMA of a segment starts from C = 0
+__device__ __forceinline__ void imma(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void imma_z(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+__device__ __forceinline__ half silu_h(half x)
+{
+    // same fp16 sequence as the reference (q4_mlp.cu:27-36)
+    const half one = __float2half(1.0f);
+    const half e = hexp(__hneg(x));
+    const half r = hrcp(__hadd(one, e));
+    return __hmul(x, r);
+}
+
+// One k8-row (8 halves) -> 16-bit integers x_q = 256 a + b with BOTH bytes signed (b = sign-extended low byte,
+// a = (x_q + 128) >> 8), packed {a(0,2,4,6), a(1,3,5,7), b(0,2,4,6), b(1,3,5,7)}; returns sum of x_q.  |x_q| <= 32639 keeps a in s8.
+__device__ __forceinline__ int quantise_row(const uint4& hv, float inv, uint4& o)
+{
+    const half2* h = reinterpret_cast<const half2*>(&hv);
+    int sum = 0;
+    o = make_uint4(0, 0, 0, 0);
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(h[i]);
+        const int q0 = __float2int_rn(f.x * inv), q1 = __float2int_rn(f.y * inv);
+        sum += q0 + q1;
+        o.x |= (uint32_t)(((q0 + 128) >> 8) & 0xff) << (8 * i);
+        o.y |= (uint32_t)(((q1 + 128) >> 8) & 0xff) << (8 * i);
+        o.z |= (uint32_t)(q0 & 0xff) << (8 * i);
+        o.w |= (uint32_t)(q1 & 0xff) << (8 * i);
+    }
+    return sum;
+}
+__device__ __forceinline__ float row_absmax(const uint4& hv)
+{
+    const half2* h = reinterpret_cast<const half2*>(&hv);
+    float mx = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(__habs2(h[i])); mx = fmaxf(mx, fmaxf(f.x, f.y)); }
+    return mx;
+}
+
+// contiguous share of n items for CTA c of G
+__device__ __forceinline__ int share_lo(long long n, int c, int G) { return (int)(n * c / G); }
+// the CTA whose share contains item u (inverse of share_lo)
+__device__ __forceinline__ int cta_of(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
+
+struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; };     // tpm: tiles per matrix
+
+__device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
+{
+    Phase p; p.kind = kind; p.acc = nullptr; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
+    if (kind == PH_QKV)       { p.spt = a.H / TILE;  p.N = a.HQ; p.nmat = 3; p.mat0 = 0; p.acc = a.acc_qkv; }
+    else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; }
+    else if (kind == PH_GU)   { p.spt = a.H / TILE;  p.N = a.I;  p.nmat = 2; p.mat0 = 4; p.acc = a.acc_gu; }
+    else if (kind == PH_DOWN) { p.spt = a.I / TILE;  p.N = a.H;  p.nmat = 1; p.mat0 = 6; p.acc = a.acc_d; }
+    if (kind == PH_ATT) {
+        const int nch = (a.past_len + 15) >> 4;
+        p.tpm = nch > 0 ? nch : 1;                          // units per head (one empty unit when there is no history)
+        p.U = a.heads * p.tpm;
+    } else if (kind == PH_HEAD) {
+        p.U = a.lm_head ? (int)(((long long)a.vocab * a.H * 2 + W_BYTES - 1) / W_BYTES) : 0;
+    } else {
+        p.tpm = p.N / TILE;
+        p.U = p.nmat * p.tpm * p.spt;
+    }
+    return p;
+}
+
+// Grid-wide barrier for the consumer threads of all CTAs (sense-reversing: count resets, generation advances; both persist
+// across launches, so graph replays need no host-side reset).
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsigned& gen, int tid)
+{
+    consumer_sync();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned want = gen + 1u;
+        const unsigned prev = atomicAdd(bar, 1u);
+        if (prev == nctas - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 1), "r"(want) : "memory");
+        } else {
+            unsigned v;
+            const unsigned long long t0 = gtime();
+            unsigned i = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1) : "memory");
+                if ((++i & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
+            } while (v != want);
+        }
+        __threadfence();
+    }
+    gen += 1u;
+    consumer_sync();
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);      // nst x STAGE_STRIDE
+    unsigned char* xs = ring + (size_t)a.nst * STAGE_STRIDE;                          // spt_max x 16 k8-rows x 16 B: quantised x planes by K stage
+    unsigned char* segt = xs + (size_t)a.spt_max * 256;                                // spt_max x 4 x {sum x_q, x scale}
+    half* xres = reinterpret_cast<half*>(segt + (size_t)a.spt_max * 32);              // [H] residual stream (fp16, as the reference keeps it)
+    float* parts = reinterpret_cast<float*>(xres + a.H);                               // [17][PART_LD] attention partials of the warps (+ the new token)
+    float* q_s = parts + 17 * PART_LD;                                                 // [128] scaled q of the current head
+    float* kn_s = q_s + TILE;                                                          // [128] newest k row (after rope)
+    float* vn_s = kn_s + TILE;                                                         // [128] newest v row
+    half* xh = reinterpret_cast<half*>(xs);                                            // HEAD: normalised x [H] (xs is free by then)
+    __shared__ __align__(8) unsigned long long full_bar[24], empty_bar[24];
+    __shared__ float s_red[DS_NCW];
+    __shared__ float s_rm;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int nst = a.nst;
+
+    if (tid == 0) {
+        for (int i = 0; i < nst; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == DS_NCW) {
+        // ============================ producer warp: the whole token's HBM stream, in schedule order ============================
+        int slot = 0; uint32_t par = 0; long long issued = 0;          // par: parity of the "empty" completion to wait for
+        const uint32_t ring_a = smem_u32(ring), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        auto acquire = [&](uint32_t tx) -> uint32_t {
+            if (issued >= nst) mbar_wait(empty0 + slot * 8, par ^ 1u);
+            if (lane == 0) mbar_expect_tx(full0 + slot * 8, tx);
+            __syncwarp();
+            return ring_a + (uint32_t)slot * STAGE_STRIDE;
+        };
+        auto advance = [&]() { issued++; if (++slot == nst) { slot = 0; par ^= 1u; } };
+        const int ngrow = a.gshift >= 2 ? 1 : (4 >> a.gshift);          // group rows per K stage (groupsize 32: 4, 64: 2, >= 128: 1)
+        #pragma unroll 1
+        for (int l = 0; l < a.n_layers; l++) {
+            const LayerDesc* L = a.layers + l;
+            #pragma unroll 1
+            for (int ph = PH_QKV; ph <= PH_DOWN; ph++) {
+                const Phase p = phase_of(a, ph);
+                const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+                if (ph == PH_ATT) {
+                    #pragma unroll 1
+                    for (int u = u0; u < u1; u++) {
+                        const int h = u / p.tpm, ch = u - h * p.tpm;
+                        const int pos0 = ch * 16;
+                        int nv = a.past_len - pos0; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
+                        const uint32_t base = acquire((uint32_t)nv * 512u);
+                        if (nv > 0) {
+                            const size_t off = ((size_t)h * a.max_seq + pos0) * TILE;
+                            if (lane == 0) bulk_g2s(base, L->kc + off, (uint32_t)nv * 256u, full0 + slot * 8);
+                            if (lane == 1) bulk_g2s(base + 4096, L->vc + off, (uint32_t)nv * 256u, full0 + slot * 8);
+                        }
+                        advance();
+                    }
+                    continue;
+                }
+                if (u1 <= u0) continue;
+                int tile = u0 / p.spt, s = u0 - tile * p.spt;
+                #pragma unroll 1
+                for (int u = u0; u < u1; u++) {
+                    const int mi = tile / p.tpm, col0 = (tile - mi * p.tpm) * TILE;
+                    const int m = p.mat0 + mi;
+                    const uint32_t base = acquire((uint32_t)W_BYTES + (uint32_t)ngrow * 320u);
+                    const uint32_t fb = full0 + slot * 8;
+                    if (lane < 4) tma_load_2d(base + lane * BOX_BYTES, &L->tm[m], col0 + lane * 32, s * 16, fb);
+                    else if (lane < 4 + ngrow) {
+                        const int r = lane - 4;
+                        const int grp = a.gshift >= 2 ? ((s * 4) >> a.gshift) : (s * ngrow + r);
+                        bulk_g2s(base + META_SC + r * 256, L->sc[m] + (size_t)grp * p.N + col0, 256u, fb);
+                    } else if (lane < 4 + 2 * ngrow) {
+                        const int r = lane - 4 - ngrow;
+                        const int grp = a.gshift >= 2 ? ((s * 4) >> a.gshift) : (s * ngrow + r);
+                        bulk_g2s(base + META_ZQ + r * 64, L->qz[m] + (size_t)grp * (p.N >> 3) + (col0 >> 3), 64u, fb);
+                    }
+                    advance();
+                    if (++s == p.spt) { s = 0; tile++; }
+                }
+            }
+        }
+        {
+            const Phase p = phase_of(a, PH_HEAD);
+            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const long long total = (long long)a.vocab * a.H * 2;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.lm_head);
+            #pragma unroll 1
+            for (int u = u0; u < u1; u++) {
+                const long long off = (long long)u * W_BYTES;
+                const uint32_t bytes = (uint32_t)((total - off) < W_BYTES ? (total - off) : W_BYTES);
+                const uint32_t base = acquire(bytes);
+                if (lane == 0) bulk_g2s(base, src + off, bytes, full0 + slot * 8);
+                advance();
+            }
+        }
+        return;
+    }
+
+    // ======================================================= consumer warps =======================================================
+    const int wn = warp & 3, wk = warp >> 2;
+    const int g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) | ((g & 1) << 2);            // column chunk of this lane (bank-conflict-free against the 128B swizzle)
+    const int lane_col = wn * 32 + 4 * pg;
+    const uint32_t ring_a = smem_u32(ring), xs_a = smem_u32(xs), seg_a = smem_u32(segt);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    long long jbase = 0;                                 // ring position of the next stage this CTA consumes (same count as the producer)
+    unsigned gen;
+    if (tid == 0) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar + 1) : "memory"); s_red[0] = __uint_as_float(v); }
+    consumer_sync();
+    gen = __float_as_uint(s_red[0]);
+    consumer_sync();
+
+    auto zero_share = [&](float* buf, int n) {            // this CTA's share of a float buffer (n % 4 == 0)
+        const int lo = share_lo(n >> 2, cta, G), hi = share_lo(n >> 2, cta + 1, G);
+        for (int i = lo + tid; i < hi; i += DS_CONSUMERS) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    // ---- launch start: all accumulators and the logits to zero (robust against an aborted previous launch), then barrier ----
+    zero_share(a.acc_qkv, 3 * a.HQ); zero_share(a.acc_o, a.H); zero_share(a.acc_gu, 2 * a.I); zero_share(a.acc_d, a.H);
+    if (a.logits) zero_share(a.logits, a.vocab);
+    for (int i = tid; i < a.H / 8; i += DS_CONSUMERS)
+        reinterpret_cast<uint4*>(xres)[i] = __ldg(reinterpret_cast<const uint4*>(a.x_in) + i);
+    grid_barrier(a.bar, (unsigned)G, gen, tid);
+
+    // ---- residual add (fp16(x + fp32 delta), the rounding point of q4_matmul's no_zero epilogue) + row factor of the RMS norm ----
+    auto residual_and_norm = [&](const float* delta) {
+        float ss = 0.f;
+        for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
+            uint4 xv = reinterpret_cast<uint4*>(xres)[i];
+            half2* h = reinterpret_cast<half2*>(&xv);
+            if (delta) {
+                const float4 d0 = ldcg4(delta + i * 8), d1 = ldcg4(delta + i * 8 + 4);
+                float2 f;
+                f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x + d0.x, f.y + d0.y);
+                f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x + d0.z, f.y + d0.w);
+                f = __half22float2(h[2]); h[2] = __floats2half2_rn(f.x + d1.x, f.y + d1.y);
+                f = __half22float2(h[3]); h[3] = __floats2half2_rn(f.x + d1.z, f.y + d1.w);
+                reinterpret_cast<uint4*>(xres)[i] = xv;
+            }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { const float2 f = __half22float2(h[j]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) s_red[warp] = ss;
+        consumer_sync();
+        if (tid == 0) {
+            float tot = 0.f;
+            #pragma unroll
+            for (int w = 0; w < DS_NCW; w++) tot += s_red[w];
+            s_rm = __half2float(__float2half_rn(rsqrtf(tot / (float)a.H + a.eps)));       // rms_norm.cu:113-116
+        }
+        consumer_sync();
+    };
+
+    // ---- quantise the K stages [s0, s0 + n) (cyclic mod spt) of the phase input into xs / segt; `get(k8)` yields 8 fp16 values ----
+    const int rpg = a.gshift >= 2 ? 16 : (4 << a.gshift);          // k8-rows per quantisation segment (a segment never spans stages)
+    auto stage_x = [&](int s0, int n, int spt, auto get) {
+        const int nrows = n * 16;
+        for (int base = 0; base < nrows; base += DS_CONSUMERS) {
+            const int r = base + tid;
+            const bool act = r < nrows;
+            int s = s0 + (r >> 4); if (s >= spt) s -= spt;
+            const int rr = r & 15;
+            const uint4 hv = act ? get(s * 16 + rr) : make_uint4(0, 0, 0, 0);
+            float mx = row_absmax(hv);
+            for (int o = rpg >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            uint4 q;
+            int sum = quantise_row(hv, mx > 0.f ? 32639.0f / mx : 0.f, q);
+            for (int o = rpg >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (act) {
+                *reinterpret_cast<uint4*>(xs + (size_t)s * 256 + rr * 16) = q;
+                if ((rr & (rpg - 1)) == 0)
+                    *reinterpret_cast<float2*>(segt + (size_t)s * 32 + (rr / rpg) * 8) = make_float2(__int_as_float(sum), mx * (1.0f / 32639.0f));
+            }
+        }
+    };
+
+    // ---- GEMV phase body: this warp's stages of the CTA's unit range ----
+    auto gemv = [&](const Phase& p, int u0, int u1) {
+        const int n = u1 - u0;
+        int i = (int)((wk - jbase) & 3);                     // stage j of the CTA goes to k-warp group j & 3
+        if (i >= n) return;
+        long long j = jbase + i;
+        int slot = (int)(j % nst); uint32_t par = (uint32_t)((j / nst) & 1);
+        int tile = (u0 + i) / p.spt, s = (u0 + i) - tile * p.spt;
+        int cur_tile = tile;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int ia[8];
+        const int upseg = rpg >> 2;                          // units (of 4 k8-rows) per quantisation segment: 1, 2 or 4
+        auto flush_tile = [&]() {
+            if (t == 0) {
+                const int mi = cur_tile / p.tpm, col0 = (cur_tile - mi * p.tpm) * TILE;
+                red_add_v4(p.acc + (size_t)mi * p.N + col0 + lane_col, acc[0], acc[1], acc[2], acc[3]);
+            }
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        };
+        for (; i < n; i += 4) {
+            if (tile != cur_tile) { flush_tile(); cur_tile = tile; }
+            mbar_wait(full0 + slot * 8, par);
+            const uint32_t sb = ring_a + (uint32_t)slot * STAGE_STRIDE;
+            const uint32_t xrow = xs_a + (uint32_t)s * 256u + (uint32_t)t * 16u + (uint32_t)(g & 1) * 8u;
+            int (&aA)[4] = *reinterpret_cast<int (*)[4]>(&ia[0]);
+            int (&aB)[4] = *reinterpret_cast<int (*)[4]>(&ia[4]);
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int r = u * 4 + t;                    // k8-row of this lane inside the stage
+                const uint4 w = lds128(sb + wn * BOX_BYTES + r * 128 + ((pg ^ (r & 7)) << 4));
+                uint2 xv = lds64(xrow + u * 64);
+                if (g >= 2) xv = make_uint2(0u, 0u);        // B column g: 0 = high-byte plane, 1 = low-byte plane, others unused
+                const uint32_t M4 = 0x0f0f0f0fu;
+                const uint32_t lo0 = w.x & M4, hi0 = (w.x >> 4) & M4, lo1 = w.y & M4, hi1 = (w.y >> 4) & M4;
+                const uint32_t lo2 = w.z & M4, hi2 = (w.z >> 4) & M4, lo3 = w.w & M4, hi3 = (w.w >> 4) & M4;
+                if ((u & (upseg - 1)) == 0) {
+                    imma_z(aA, lo0, lo1, hi0, hi1, xv.x, xv.y);
+                    imma_z(aB, lo2, lo3, hi2, hi3, xv.x, xv.y);
+                } else {
+                    imma(aA, lo0, lo1, hi0, hi1, xv.x, xv.y);
+                    imma(aB, lo2, lo3, hi2, hi3, xv.x, xv.y);
+                }
+                if (((u + 1) & (upseg - 1)) == 0) {
+                    // segment complete: acc += scale * sx * (256 * sum a q + sum b q - zp * sum x_q)
+                    const int seg = u / upseg;
+                    const int row = a.gshift >= 2 ? 0 : seg;
+                    const uint2 sc2 = lds64(sb + META_SC + row * 256 + lane_col * 2);
+                    const uint32_t zw = lds32(sb + META_ZQ + row * 64 + (lane_col >> 3) * 4);
+                    const uint2 sg = lds64(seg_a + (uint32_t)s * 32u + (uint32_t)seg * 8u);
+                    const int sxq = (int)sg.x; const float sx = __uint_as_float(sg.y);
+                    const half2 s01 = *reinterpret_cast<const half2*>(&sc2.x), s23 = *reinterpret_cast<const half2*>(&sc2.y);
+                    const float cs4[4] = {__low2float(s01), __high2float(s01), __low2float(s23), __high2float(s23)};
+                    const uint32_t z4 = zw >> ((lane_col & 4) * 4);
+                    #pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        // lane t == 0: D(row g / g+8, col 0 = plane a, col 1 = plane b); column c of this lane = MMA (c >> 1), row half (c & 1)
+                        const int jj = (c >> 1) * 4 + (c & 1) * 2;
+                        const int zp = (int)((z4 >> (4 * c)) & 0xfu) + 1;
+                        const int val = ia[jj] * 256 + ia[jj + 1] - zp * sxq;
+                        acc[c] = fmaf(cs4[c] * sx, (float)val, acc[c]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + slot * 8);
+            slot += 4; if (slot >= nst) { slot -= nst; par ^= 1u; }
+            s += 4; while (s >= p.spt) { s -= p.spt; tile++; }
+        }
+        flush_tile();
+    };
+
+    #pragma unroll 1
+    for (int l = 0; l < a.n_layers; l++) {
+        const LayerDesc* L = a.layers + l;
+        // ======================================================== QKV ========================================================
+        {
+            const Phase p = phase_of(a, PH_QKV);
+            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            if (l > 0) zero_share(a.acc_gu, 2 * a.I);
+            residual_and_norm(l > 0 ? a.acc_d : nullptr);
+            if (u1 > u0) {
+                const half* nw = L->ln1;
+                const half2 rm2 = __float2half2_rn(s_rm);
+                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
+                    uint4 xv = reinterpret_cast<const uint4*>(xres)[k8];
+                    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(nw) + k8);
+                    half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) h[i] = __hmul2(__hmul2(h[i], rm2), w2[i]);      // rms_norm.cu:118-131
+                    return xv;
+                });
+            }
+            consumer_sync();
+            gemv(p, u0, u1);
+            jbase += u1 - u0;
+        }
+        grid_barrier(a.bar, (unsigned)G, gen, tid);
+
+        // ======================================================== ATT ========================================================
+        {
+            const Phase p = phase_of(a, PH_ATT);
+            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            if (l > 0) zero_share(a.acc_d, a.H);
+            const int nph = p.tpm;
+            const float scale = rsqrtf((float)TILE);
+            const int l16 = lane & 15, sub = lane >> 4;
+            for (int h = (u1 > u0 ? u0 / nph : 0); u1 > u0 && h * nph < u1; h++) {
+                const int ua = max(u0, h * nph), ub = min(u1, (h + 1) * nph);
+                const bool owner = ub == (h + 1) * nph;            // this CTA holds the head's last chunk: it also takes the new token
+                consumer_sync();                                   // previous segment's parts / q_s consumed
+                if (tid < TILE) {
+                    // q (and k) of this head: fp16 projection result, rope in fp16 with the reference's instruction order (rope.cu:48-67)
+                    const half* sr = a.sin + (size_t)a.past_len * TILE;
+                    const half* cr = a.cos + (size_t)a.past_len * TILE;
+                    const float* aq = a.acc_qkv + (size_t)h * TILE;
+                    const half qv = __float2half_rn(__ldcg(aq + tid)), qo = __float2half_rn(__ldcg(aq + (tid ^ 64)));
+                    const half sn = tid < 64 ? __hneg(sr[tid]) : sr[tid];
+                    q_s[tid] = __half2float(__hfma(qv, cr[tid], __hmul(qo, sn))) * scale;
+                    if (owner) {
+                        const float* ak = a.acc_qkv + a.HQ + (size_t)h * TILE;
+                        const half kv = __float2half_rn(__ldcg(ak + tid)), ko = __float2half_rn(__ldcg(ak + (tid ^ 64)));
+                        const half kr = __hfma(kv, cr[tid], __hmul(ko, sn));
+                        const half vv = __float2half_rn(__ldcg(a.acc_qkv + 2 * a.HQ + (size_t)h * TILE + tid));
+                        kn_s[tid] = __half2float(kr); vn_s[tid] = __half2float(vv);
+                        const size_t off = ((size_t)h * a.max_seq + a.past_len) * TILE + tid;      // cache layout q4_attn.cu:32-51
+                        L->kc[off] = kr; L->vc[off] = vv;
+                    }
+                }
+                consumer_sync();
+                float qf[8];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) qf[j] = q_s[l16 * 8 + j];
+                float m = -INFINITY, lsum = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+                // stages of this segment: local indices [ua - u0, ub - u0); stage j of the CTA goes to warp j & 15
+                int i = (ua - u0) + (int)((warp - (jbase + (ua - u0))) & 15);
+                if (i < ub - u0) {
+                    long long j = jbase + i;
+                    int slot = (int)(j % nst); uint32_t par = (uint32_t)((j / nst) & 1);
+                    for (; i < ub - u0; i += 16) {
+                        const int ch = (u0 + i) - h * nph;
+                        int nv = a.past_len - ch * 16; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
+                        mbar_wait(full0 + slot * 8, par);
+                        const uint32_t sb = ring_a + (uint32_t)slot * STAGE_STRIDE;
+                        float sc8[8];
+                        float smax = -INFINITY;
+                        #pragma unroll
+                        for (int it = 0; it < 8; it++) {
+                            const int pp = it * 2 + sub;
+                            const uint4 kv = lds128(sb + pp * 256 + l16 * 16);
+                            const half2* hh = reinterpret_cast<const half2*>(&kv);
+                            float d = 0.f;
+                            #pragma unroll
+                            for (int q = 0; q < 4; q++) { const float2 f = __half22float2(hh[q]); d = fmaf(f.x, qf[2 * q], d); d = fmaf(f.y, qf[2 * q + 1], d); }
+                            d += __shfl_xor_sync(0xffffffffu, d, 8); d += __shfl_xor_sync(0xffffffffu, d, 4);
+                            d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 1);
+                            sc8[it] = pp < nv ? d : -INFINITY;
+                            smax = fmaxf(smax, sc8[it]);
+                        }
+                        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 16));
+                        if (nv > 0) {
+                            const float mnew = fmaxf(m, smax);
+                            const float alpha = __expf(m - mnew);
+                            float psum = 0.f;
+                            #pragma unroll
+                            for (int it = 0; it < 8; it++) { sc8[it] = __expf(sc8[it] - mnew); psum += sc8[it]; }
+                            psum += __shfl_xor_sync(0xffffffffu, psum, 16);
+                            lsum = lsum * alpha + psum;
+                            #pragma unroll
+                            for (int c = 0; c < 4; c++) o[c] *= alpha;
+                            m = mnew;
+                            #pragma unroll
+                            for (int pp = 0; pp < 16; pp++) {
+                                const float w = __shfl_sync(0xffffffffu, sc8[pp >> 1], (pp & 1) * 16);
+                                if (pp < nv) {
+                                    const uint2 vv = lds64(sb + 4096 + pp * 256 + lane * 8);
+                                    const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&vv.x));
+                                    const float2 f1 = __half22float2(*reinterpret_cast<const half2*>(&vv.y));
+                                    o[0] = fmaf(w, f0.x, o[0]); o[1] = fmaf(w, f0.y, o[1]); o[2] = fmaf(w, f1.x, o[2]); o[3] = fmaf(w, f1.y, o[3]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane < 4) mbar_arrive(empty0 + slot * 8);
+                        slot += 16; while (slot >= nst) { slot -= nst; par ^= 1u; }
+                    }
+                }
+                {
+                    float* pw = parts + warp * PART_LD;
+                    *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (lane == 0) { pw[128] = m; pw[129] = lsum; }
+                }
+                if (owner && warp == 0) {
+                    // the new token itself: score q . k_new, weight 1 in its own partial
+                    float d = 0.f;
+                    #pragma unroll
+                    for (int c = 0; c < 4; c++) d = fmaf(q_s[lane * 4 + c], kn_s[lane * 4 + c], d);
+                    #pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                    float* pw = parts + 16 * PART_LD;
+                    *reinterpret_cast<float4*>(pw + lane * 4) = *reinterpret_cast<const float4*>(vn_s + lane * 4);
+                    if (lane == 0) { pw[128] = d; pw[129] = 1.0f; }
+                }
+                consumer_sync();
+                if (tid < TILE) {
+                    const int np = owner ? 17 : 16;
+                    float M = -INFINITY;
+                    for (int w = 0; w < np; w++) M = fmaxf(M, parts[w * PART_LD + 128]);
+                    float Lt = 0.f, ov = 0.f;
+                    for (int w = 0; w < np; w++) {
+                        const float mw = parts[w * PART_LD + 128];
+                        const float wgt = mw == -INFINITY ? 0.f : __expf(mw - M);
+                        Lt = fmaf(parts[w * PART_LD + 129], wgt, Lt);
+                        ov = fmaf(parts[w * PART_LD + tid], wgt, ov);
+                    }
+                    const int slot_id = cta - cta_of((long long)h * nph, p.U, G);
+                    float* dst = a.att_part + ((size_t)h * a.att_slots + slot_id) * PART_LD;
+                    dst[tid] = ov;
+                    if (tid == 0) { dst[128] = M; dst[129] = Lt; }
+                }
+            }
+            jbase += u1 - u0;
+        }
+        grid_barrier(a.bar, (unsigned)G, gen, tid);
+
+        // ========================================================= O =========================================================
+        {
+            const Phase p = phase_of(a, PH_O);
+            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            zero_share(a.acc_qkv, 3 * a.HQ);
+            if (u1 > u0) {
+                const Phase pa = phase_of(a, PH_ATT);
+                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
+                    // softmax-combine of the CTA partials of head k8 / 16 (model.py:402-409), 8 dims per thread, fp16 result
+                    const int h = k8 >> 4, d0 = (k8 & 15) * 8;
+                    const int c_lo = cta_of((long long)h * pa.tpm, pa.U, G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, G);
+                    const float* src = a.att_part + (size_t)h * a.att_slots * PART_LD;
+                    float M = -INFINITY;
+                    for (int sl = 0; sl <= c_hi - c_lo; sl++) M = fmaxf(M, __ldcg(src + sl * PART_LD + 128));
+                    float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int sl = 0; sl <= c_hi - c_lo; sl++) {
+                        const float mw = __ldcg(src + sl * PART_LD + 128);
+                        const float wgt = mw == -INFINITY ? 0.f : __expf(mw - M);
+                        Lt = fmaf(__ldcg(src + sl * PART_LD + 129), wgt, Lt);
+                        const float4 o0 = ldcg4(src + sl * PART_LD + d0), o1 = ldcg4(src + sl * PART_LD + d0 + 4);
+                        ov[0] = fmaf(o0.x, wgt, ov[0]); ov[1] = fmaf(o0.y, wgt, ov[1]); ov[2] = fmaf(o0.z, wgt, ov[2]); ov[3] = fmaf(o0.w, wgt, ov[3]);
+                        ov[4] = fmaf(o1.x, wgt, ov[4]); ov[5] = fmaf(o1.y, wgt, ov[5]); ov[6] = fmaf(o1.z, wgt, ov[6]); ov[7] = fmaf(o1.w, wgt, ov[7]);
+                    }
+                    const float inv = 1.0f / Lt;
+                    uint4 r; half2* hh = reinterpret_cast<half2*>(&r);
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) hh[i] = __floats2half2_rn(ov[2 * i] * inv, ov[2 * i + 1] * inv);
+                    return r;
+                });
+            }
+            consumer_sync();
+            gemv(p, u0, u1);
+            jbase += u1 - u0;
+        }
+        grid_barrier(a.bar, (unsigned)G, gen, tid);
+
+        // ========================================================= GU ========================================================
+        {
+            const Phase p = phase_of(a, PH_GU);
+            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            residual_and_norm(a.acc_o);
+            if (u1 > u0) {
+                const half* nw = L->ln2;
+                const half2 rm2 = __float2half2_rn(s_rm);
+                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
+                    uint4 xv = reinterpret_cast<const uint4*>(xres)[k8];
+                    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(nw) + k8);
+                    half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) h[i] = __hmul2(__hmul2(h[i], rm2), w2[i]);
+                    return xv;
+                });
+            }
+            consumer_sync();
+            gemv(p, u0, u1);
+            jbase += u1 - u0;
+        }
+        grid_barrier(a.bar, (unsigned)G, gen, tid);
+
+        // ======================================================== DOWN =======================================================
+        {
+            const Phase p = phase_of(a, PH_DOWN);
+            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            zero_share(a.acc_o, a.H);
+            if (u1 > u0) {
+                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
+                    // silu(gate) * up on the fp16-rounded projections (q4_mlp.cu:27-36,46-88)
+                    const float4 g0 = ldcg4(a.acc_gu + k8 * 8), g1 = ldcg4(a.acc_gu + k8 * 8 + 4);
+                    const float4 u0v = ldcg4(a.acc_gu + a.I + k8 * 8), u1v = ldcg4(a.acc_gu + a.I + k8 * 8 + 4);
+                    const float gf[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    const float uf[8] = {u0v.x, u0v.y, u0v.z, u0v.w, u1v.x, u1v.y, u1v.z, u1v.w};
+                    uint4 r; half* hh = reinterpret_cast<half*>(&r);
+                    #pragma unroll
+                    for (int i = 0; i < 8; i++) hh[i] = __hmul(silu_h(__float2half_rn(gf[i])), __float2half_rn(uf[i]));
+                    return r;
+                });
+            }
+            consumer_sync();
+            gemv(p, u0, u1);
+            jbase += u1 - u0;
+        }
+        grid_barrier(a.bar, (unsigned)G, gen, tid);
+    }
+
+    // ========================================================= HEAD ==========================================================
+    residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr);
+    if (a.x_out && cta == 0)
+        for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
+    if (a.lm_head) {
+        const Phase p = phase_of(a, PH_HEAD);
+        const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+        {
+            const half2 rm2 = __float2half2_rn(s_rm);
+            for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
+                uint4 xv = reinterpret_cast<const uint4*>(xres)[i];
+                const uint4 wv = __ldg(reinterpret_cast<const uint4*>(a.final_norm) + i);
+                half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
+                #pragma unroll
+                for (int q = 0; q < 4; q++) h[q] = __hmul2(__hmul2(h[q], rm2), w2[q]);
+                reinterpret_cast<uint4*>(xh)[i] = xv;
+            }
+        }
+        consumer_sync();
+        // stage = 8 chunks of 512 fp16 of the row-major [vocab, H] matrix; stage j of the CTA goes to warp j & 15
+        const int cpr = a.H >> 9;                               // chunks per vocabulary row
+        const long long nchunks = (long long)a.vocab * cpr;
+        int i = (int)((warp - jbase) & 15);
+        if (i < u1 - u0) {
+            long long j = jbase + i;
+            int slot = (int)(j % nst); uint32_t par = (uint32_t)((j / nst) & 1);
+            const uint32_t xh_a = smem_u32(xh);
+            for (; i < u1 - u0; i += 16) {
+                mbar_wait(full0 + slot * 8, par);
+                const uint32_t sb = ring_a + (uint32_t)slot * STAGE_STRIDE;
+                const long long c0 = (long long)(u0 + i) * 8;
+                long long row = c0 / cpr; int kc = (int)(c0 - row * cpr);
+                float part = 0.f;
+                #pragma unroll 1
+                for (int cc = 0; cc < 8 && c0 + cc < nchunks; cc++) {
+                    #pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        const uint4 wv = lds128(sb + cc * 1024 + hf * 512 + lane * 16);
+                        const uint4 xv = lds128(xh_a + (uint32_t)kc * 1024u + hf * 512 + lane * 16);
+                        const half2* wh = reinterpret_cast<const half2*>(&wv); const half2* xq = reinterpret_cast<const half2*>(&xv);
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float2 fw = __half22float2(wh[q]), fx = __half22float2(xq[q]);
+                            part = fmaf(fw.x, fx.x, part); part = fmaf(fw.y, fx.y, part);
+                        }
+                    }
+                    if (++kc == cpr || cc == 7 || c0 + cc + 1 == nchunks) {
+                        float tot = part;
+                        #pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                        if (lane == 0) atomicAdd(a.logits + row, tot);
+                        part = 0.f;
+                        if (kc == cpr) { kc = 0; row++; }
+                    }
+                }
+                __syncwarp();
+                if (lane < 4) mbar_arrive(empty0 + slot * 8);
+                slot += 16; while (slot >= nst) { slot -= nst; par ^= 1u; }
+            }
+        }
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------------
+struct exl_decode_plan
+{
+    int device = 0;
+    StepArgs args;
+    LayerDesc* d_layers = nullptr;
+    unsigned char* d_scratch = nullptr;
+    size_t smem = 0;
+    int grid = 0;
+};
+
+static int plan_fail(exl_decode_plan* p, int rc) { if (p) { if (p->d_layers) cudaFree(p->d_layers); if (p->d_scratch) cudaFree(p->d_scratch); delete p; } return rc; }
+
+extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan** out)
+{
+    if (!d || !out) return exl_set_err(EXL_ERR_ARG, "decode_plan: NULL argument");
+    *out = nullptr;
+    if (d->n_layers < 1 || d->n_layers > MAX_LAYERS || !d->mats || !d->mats[0]) return exl_set_err(EXL_ERR_ARG, "decode_plan: bad layer count %d", d->n_layers);
+    const exl_q4_matrix* q0 = d->mats[0];
+    ExlDevice* ds = exl_device_state(q0->device);
+    if (!ds) return EXL_ERR_CUDA;
+    DeviceGuard guard(q0->device);
+    const int H = q0->K, HQ = q0->N, I = d->mats[4]->N;
+    if (d->head_dim != TILE || d->num_heads * TILE != HQ) return exl_set_err(EXL_ERR_ARG, "decode_plan: head_dim must be 128 and heads * 128 == q_proj width (%d heads, width %d)", d->num_heads, HQ);
+    if (H % 512 || HQ % TILE || I % TILE) return exl_set_err(EXL_ERR_ARG, "decode_plan: widths must be multiples of 128 (hidden of 512): hidden %d attn %d inter %d", H, HQ, I);
+    const int gs = q0->groupsize;
+    int gs32 = gs / 32, sh = 0;
+    if (q0->groups > 1) {
+        if (gs % 32 || (gs32 & (gs32 - 1))) return exl_set_err(EXL_ERR_ARG, "decode_plan: groupsize %d must be 32 * 2^n", gs);
+        while ((1 << sh) < gs32) sh++;
+    } else sh = 30;
+    std::vector<LayerDesc> L((size_t)d->n_layers);
+    const int expectK[7] = {H, H, H, HQ, H, H, I}, expectN[7] = {HQ, HQ, HQ, H, I, I, H};
+    for (int l = 0; l < d->n_layers; l++) {
+        memset(&L[l], 0, sizeof(LayerDesc));
+        for (int i = 0; i < 7; i++) {
+            const exl_q4_matrix* w = d->mats[l * 7 + i];
+            if (!w) return exl_set_err(EXL_ERR_STATE, "decode_plan: NULL handle (layer %d matrix %d)", l, i);
+            if (w->x_map) return exl_set_err(EXL_ERR_ARG, "decode_plan: act-order matrices are not supported by the fused step (use the per-op path)");
+            if (w->K != expectK[i] || w->N != expectN[i] || w->device != q0->device)
+                return exl_set_err(EXL_ERR_ARG, "decode_plan: layer %d matrix %d is %d x %d, expected %d x %d", l, i, w->K, w->N, expectK[i], expectN[i]);
+            const bool one = q0->groups == 1;
+            if ((one && w->groups != 1) || (!one && w->groupsize != gs)) return exl_set_err(EXL_ERR_ARG, "decode_plan: mixed group sizes");
+            L[l].tm[i] = w->tmap_w; L[l].qz[i] = w->qzeros; L[l].sc[i] = w->scales;
+        }
+        L[l].ln1 = (const half*)d->ln1[l]; L[l].ln2 = (const half*)d->ln2[l];
+        L[l].kc = (half*)d->key_cache[l]; L[l].vc = (half*)d->value_cache[l];
+    }
+    exl_decode_plan* p = new exl_decode_plan();
+    p->device = q0->device;
+    StepArgs& a = p->args;
+    memset(&a, 0, sizeof(a));
+    a.n_layers = d->n_layers; a.H = H; a.HQ = HQ; a.I = I; a.heads = d->num_heads; a.max_seq = d->max_seq_len; a.gshift = sh;
+    a.eps = d->rms_eps; a.sin = (const half*)d->sin; a.cos = (const half*)d->cos;
+    a.final_norm = (const half*)d->final_norm; a.lm_head = (const half*)d->lm_head; a.vocab = d->lm_head ? d->vocab : 0;
+    if (d->lm_head && (!d->final_norm || d->vocab % 4)) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: lm_head needs final_norm and vocab %% 4 == 0"));
+    a.spt_max = (H > I ? H : I) / TILE; if (HQ / TILE > a.spt_max) a.spt_max = HQ / TILE;
+    int dev_smem = 0;
+    cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+    const size_t fixed = 1024 + (size_t)a.spt_max * (256 + 32) + (size_t)H * 2 + (size_t)(17 * PART_LD + 3 * TILE) * 4 + 1024 /* static */;
+    int nst = (int)(((size_t)dev_smem - fixed) / STAGE_STRIDE);
+    if (const char* e = getenv("EXL_DS_NST")) { int v = atoi(e); if (v >= 4 && v < nst) nst = v; }
+    if (nst > 20) nst = 20;
+    if (nst < 6) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: model too wide for the shared-memory plan (ring of %d stages)", nst));
+    a.nst = nst;
+    p->smem = fixed - 1024 + (size_t)nst * STAGE_STRIDE;
+    if ((size_t)H * 2 > (size_t)a.spt_max * 256) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: internal: head staging does not fit"));
+    cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e != cudaSuccess) return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: smem attribute (%zu B): %s", p->smem, cudaGetErrorString(e)));
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel, DS_THREADS, p->smem);
+    if (e != cudaSuccess || per_sm < 1) return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: kernel does not fit an SM (smem %zu)", p->smem));
+    p->grid = ds->num_sms;
+    if (const char* eg = getenv("EXL_DS_GRID")) { int v = atoi(eg); if (v >= 1 && v <= ds->num_sms) p->grid = v; }
+    a.att_slots = p->grid / (d->num_heads > 0 ? d->num_heads : 1) + 2;
+    // scratch: accumulators | attention partials | barrier
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_qkv = take((size_t)3 * HQ * 4), o_o = take((size_t)H * 4), o_gu = take((size_t)2 * I * 4), o_d = take((size_t)H * 4);
+    const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256);
+    if (cudaMalloc(&p->d_scratch, off) != cudaSuccess || cudaMalloc(&p->d_layers, sizeof(LayerDesc) * L.size()) != cudaSuccess)
+        return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: cudaMalloc failed"));
+    if (cudaMemset(p->d_scratch, 0, off) != cudaSuccess ||
+        cudaMemcpy(p->d_layers, L.data(), sizeof(LayerDesc) * L.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: upload failed"));
+    a.layers = p->d_layers;
+    a.acc_qkv = (float*)(p->d_scratch + o_qkv); a.acc_o = (float*)(p->d_scratch + o_o); a.acc_gu = (float*)(p->d_scratch + o_gu);
+    a.acc_d = (float*)(p->d_scratch + o_d); a.att_part = (float*)(p->d_scratch + o_att); a.bar = (unsigned*)(p->d_scratch + o_bar);
+    *out = p;
+    return EXL_OK;
+}
+
+extern "C" int exl_decode_plan_destroy(exl_decode_plan* p)
+{
+    if (!p) return EXL_OK;
+    DeviceGuard guard(p->device);
+    cudaDeviceSynchronize();
+    plan_fail(p, 0);
+    return EXL_OK;
+}
+
+extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step)
+{
+    if (!p) return exl_set_err(EXL_ERR_STATE, "decode_plan_info: NULL plan");
+    if (grid) *grid = p->grid; if (ring_stages) *ring_stages = p->args.nst; if (smem_bytes) *smem_bytes = (int64_t)p->smem;
+    if (barriers_per_step) *barriers_per_step = 1 + 5 * (int64_t)p->args.n_layers;
+    return EXL_OK;
+}
+
+extern "C" int exl_decode_step(exl_decode_plan* p, const void* x_in, int past_len, void* x_out, void* logits, void* stream_)
+{
+    if (!p) return exl_set_err(EXL_ERR_STATE, "decode_step: NULL plan");
+    if (!x_in) return exl_set_err(EXL_ERR_ARG, "decode_step: x_in is NULL");
+    if (past_len < 0 || past_len >= p->args.max_seq) return exl_set_err(EXL_ERR_ARG, "decode_step: past_len %d outside the cache (max_seq %d)", past_len, p->args.max_seq);
+    if (p->args.lm_head && !logits) return exl_set_err(EXL_ERR_ARG, "decode_step: the plan has an lm_head, logits must be given");
+    DeviceGuard guard(p->device);
+    StepArgs a = p->args;
+    a.x_in = (const half*)x_in; a.x_out = (half*)x_out; a.logits = (float*)logits; a.past_len = past_len;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;      // all CTAs co-resident: the grid barrier relies on it
+    cfg.gridDim = dim3((unsigned)p->grid); cfg.blockDim = dim3(DS_THREADS); cfg.dynamicSmemBytes = p->smem; cfg.stream = (cudaStream_t)stream_;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_kernel, a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return exl_set_err(EXL_ERR_CUDA, "launch of decode_step_kernel failed: %s (grid %d, smem %zu)", cudaGetErrorString(e), p->grid, p->smem);
+    return EXL_OK;
+}

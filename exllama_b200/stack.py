@@ -187,6 +187,27 @@ class DecodeStack:
         hn = cuda_ext.ext_rms_norm(hidden, self.norm, s.eps)
         return torch.matmul(hn.view(-1, s.hidden), self.lm_head.t()).float()
 
+    # ---- decode: the whole token as ONE persistent kernel (csrc/decode_step.cu) -------------------
+    def make_plan(self, with_head=True):
+        """Build the exl_decode_plan over this stack's handles, norms, caches and tables (borrowed)."""
+        from . import capi
+        if self.tp_size != 1:
+            raise NotImplementedError("the fused decode step is single-GPU")
+        hs = [[L.q.q4, L.k.q4, L.v.q4, L.o.q4, L.gate.q4, L.up.q4, L.down.q4] for L in self.layers]
+        head = self.lm_head if with_head else None
+        self.dplan = capi.DecodePlan(hs, [L.ln1 for L in self.layers], [L.ln2 for L in self.layers], self.key_cache, self.value_cache,
+                                    self.sin, self.cos, self.local_heads, self.shape.head_dim, self.max_seq, self.shape.eps,
+                                    final_norm=self.norm if head is not None else None, lm_head=head)
+        self._plan_xout = torch.empty(self.shape.hidden, dtype=torch.float16, device=self.device)
+        self._plan_logits = torch.empty((1, self.shape.vocab), dtype=torch.float32, device=self.device) if head is not None else None
+        return self.dplan
+
+    def decode_step_fused(self, hidden, past_len):
+        """hidden: [1, 1, hidden] fp16 (read only).  Returns logits [1, vocab] fp32 (or the final hidden state without a head);
+        the final pre-norm hidden state is left in self._plan_xout."""
+        self.dplan.step(hidden, past_len, x_out=self._plan_xout, logits=self._plan_logits)
+        return self._plan_logits if self._plan_logits is not None else self._plan_xout
+
     def _o_input(self, attn_local):
         """o_proj input of this rank: its own heads' output, or -- act-order + TP -- the rows of its group range out of the
         all-gathered attention output (the one extra exchange act-order costs, SURVEY.md 8e hazard 1)."""

@@ -156,6 +156,36 @@ int exl_q4_mlp(void* x, const void* rms_norm_weight, float epsilon,
 int exl_decode_attn(const void* q, const void* key_cache, const void* value_cache, void* out,
                     int num_heads, int num_kv_heads, int head_dim, int seq_len, int max_seq_len, void* stream);
 
+/* --- whole decode step as ONE persistent kernel (SURVEY.md 8f-4 "host loop"; 8f-2 lm_head + final norm) ------------- */
+
+/* Everything ExLlama.forward does for one new token of one sequence (model.py:1053-1077: per layer ExLlamaAttention.fused
+   :322-417 and ExLlamaMLP.fused :238-263, then the final norm and lm_head), in one cooperative launch -- see
+   exllama_b200/csrc/decode_step.cu.  The plan borrows every pointer in the descriptor (weights, norms, caches, tables);
+   they must stay valid and fixed for the plan's lifetime.  Restrictions: head_dim 128, kv_heads == heads, no act-order,
+   groupsize 32 * 2^n (or one group), widths multiples of 128; anything else -> EXL_ERR_ARG (use the per-op entry points). */
+typedef struct exl_decode_plan exl_decode_plan;
+typedef struct exl_decode_desc {
+    int n_layers, num_heads, head_dim, max_seq_len, vocab;
+    float rms_eps;
+    const exl_q4_matrix* const* mats;   /* [n_layers * 7]: q, k, v, o, gate, up, down of each layer (handles from exl_make_q4) */
+    const void* const* ln1;              /* [n_layers] input_layernorm weight, half [hidden] */
+    const void* const* ln2;              /* [n_layers] post_attention_layernorm weight */
+    void* const* key_cache;              /* [n_layers] half [num_heads, max_seq_len, head_dim] (model.py:557-585) */
+    void* const* value_cache;
+    const void* sin; const void* cos;    /* half [max_seq_len, head_dim] (model.py:864-877) */
+    const void* final_norm;              /* half [hidden] or NULL */
+    const void* lm_head;                 /* half [vocab, hidden] (nn.Linear weight, model.py:845-846) or NULL: no head */
+} exl_decode_desc;
+
+int exl_decode_plan_create(const exl_decode_desc* desc, exl_decode_plan** out_plan);
+int exl_decode_plan_destroy(exl_decode_plan* plan);
+int exl_decode_plan_info(const exl_decode_plan* plan, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step);
+
+/* One token: x_in half [hidden] (the embedding row), attends over cache rows [0, past_len) plus the new row, which it
+   writes at past_len.  x_out (optional) receives the final hidden state before the final norm, logits float [vocab]
+   (required iff the plan has an lm_head).  CUDA-graph capturable; successive calls need no host synchronisation. */
+int exl_decode_step(exl_decode_plan* plan, const void* x_in, int past_len, void* x_out, void* logits, void* stream);
+
 /* --- tensor-parallel variants (new functionality; the reference has no tensor parallelism) ----- */
 
 /* As exl_q4_attn_2 / exl_q4_mlp, but with add_residual == 0 the row-parallel projection OVERWRITES x with this rank's

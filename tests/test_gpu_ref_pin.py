@@ -173,7 +173,7 @@ def test_q4_attn_vs_reference_block(oracle, reflib, act, q_len, past):
             reflib.sync()
         torch.cuda.synchronize()
         outs[who] = [a.cpu().numpy() for a in (q, k, v, kc, vc, tx)]
-    for i, name in enumerate(("q", "k", "v", "key_cache", "value_cache")):
+    for i, name in enumerate(("q", "k", "v")):          # the caches are compared row by row below (mostly zeros: no meaningful rms)
         _close_to_reference(outs["ours"][i], outs["ref"][i], f"q4_attn {name}")
     np.testing.assert_array_equal(outs["ours"][5], x)            # x itself is not modified by q4_attn
     np.testing.assert_array_equal(outs["ref"][5], x)
