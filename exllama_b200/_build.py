@@ -77,37 +77,11 @@ def build_ext(force: bool = False, verbose: bool = False) -> str:
     return EXT_SO
 
 
-def build_experimental(verbose: bool = False) -> str:
-    """libexl_b200_x.so = the product library + csrc/experimental/*.cu with -DEXL_EXPERIMENTAL (extra `exl_x_*` entry points).
-    A separate file and object directory: the default artefacts are never touched.  Load it with EXL_B200_LIB=<path>."""
-    out = os.path.join(HERE, "libexl_b200_x.so")
-    objdir = os.path.join(HERE, "_obj_x")
-    os.makedirs(objdir, exist_ok=True)
-    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES] + [os.path.join(CSRC, "experimental", "decode_layer.cu")]
-    objs, procs = [], []
-    for s in srcs:
-        o = os.path.join(objdir, os.path.basename(s) + ".o")
-        objs.append(o)
-        cmd = [NVCC] + NVCC_FLAGS + ["-DEXL_EXPERIMENTAL", "-c", s, "-o", o]
-        if verbose:
-            print(" ".join(cmd))
-        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-    for cmd, p in procs:
-        o, _ = p.communicate()
-        if p.returncode != 0:
-            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + o.decode())
-    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcublas"])
-    return out
-
-
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_lib(force, verbose)
     build_ext(force, verbose)
 
 
 if __name__ == "__main__":
-    if "--experimental" in sys.argv:
-        print("built", build_experimental(verbose=True))
-        sys.exit(0)
     build_all(force="--force" in sys.argv, verbose=True)
     print("built", LIB_SO, EXT_SO)

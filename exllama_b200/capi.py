@@ -55,6 +55,7 @@ SIGNATURES = {
     "exl_decode_plan_destroy": (i32, [vp]),
     "exl_decode_plan_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
     "exl_decode_step": (i32, [vp, vp, i32, vp, vp, vp]),
+    "exl_decode_plan_trace": (i32, [vp, vp, i64]),
     "exl_launch_count": (i64, []),
     "exl_last_q4_path": (C.c_char_p, []),
 }
@@ -257,6 +258,14 @@ class DecodePlan:
 
     def step(self, x_in, past_len, x_out=None, logits=None):
         check(lib().exl_decode_step(self.handle, _ptr(x_in), past_len, _ptr(x_out), _ptr(logits), _stream()))
+
+    def trace(self):
+        """[grid, 4 layers, 16 events] globaltimer stamps (ns) of the last launch (EXL_DS_TRACE=1 at creation)."""
+        import numpy as np
+        g = self.info()["grid"]
+        out = np.zeros((g, 4, 16), dtype=np.uint64)
+        check(lib().exl_decode_plan_trace(self.handle, out.ctypes.data_as(vp), out.size))
+        return out
 
     def close(self):
         if self.handle:

@@ -631,24 +631,3 @@ int exl_apply_rep_penalty(int vocab_size, const uint64_t* seq, float penalty_max
 }
 
 } // extern "C"
-
-#ifdef EXL_EXPERIMENTAL
-// Experimental build only (python -m exllama_b200._build --experimental -> libexl_b200_x.so); not declared in include/exl_b200.h.
-int exl_decode_layer_draft(ExlDevice* ds, const exl_q4_matrix* const* mats, half* x, const half* ln1, const half* ln2, float eps,
-                           const half* sin, const half* cos, int past_len, int max_seq, int heads, half* kc, half* vc,
-                           unsigned char* scratch, bool first_layer, cudaStream_t stream);
-
-extern "C" int exl_x_decode_layer(void* x, const exl_q4_matrix* const* mats7, const void* ln1, const void* ln2, float eps,
-                                  const void* sin, const void* cos, int past_len, int max_seq, int heads, void* kc, void* vc,
-                                  void* scratch, int first_layer, void* stream)
-{
-    if (!mats7 || !mats7[0]) return exl_set_err(EXL_ERR_STATE, "x_decode_layer: NULL handle");
-    ExlDevice* ds = exl_device_state(mats7[0]->device);
-    if (!ds) return EXL_ERR_CUDA;
-    DeviceGuard guard(mats7[0]->device);
-    return exl_decode_layer_draft(ds, mats7, (half*)x, (const half*)ln1, (const half*)ln2, eps, (const half*)sin, (const half*)cos,
-                                  past_len, max_seq, heads, (half*)kc, (half*)vc, (unsigned char*)scratch, first_layer != 0,
-                                  (cudaStream_t)stream);
-}
-#endif
-

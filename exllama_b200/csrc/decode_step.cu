@@ -39,26 +39,29 @@
 
 namespace {
 
-constexpr int DS_CONSUMERS = 512;                // 16 consumer warps: 4 across the tile's columns x 4 across K stages
-constexpr int DS_THREADS = DS_CONSUMERS + 32;    // + producer warp
+constexpr int DS_CONSUMERS = 512;                // 16 consumer warps = 4 pipelines x 4 column-warps
 constexpr int DS_NCW = DS_CONSUMERS / 32;
+constexpr int DS_NPW = 4;                        // producer warps, one per pipeline
+constexpr int DS_THREADS = DS_CONSUMERS + 32 * DS_NPW;
 constexpr int TILE = 128;                        // columns per tile == K rows per stage
 constexpr int W_BYTES = 8192;                    // packed weights of one unit: 16 k8-rows x 128 columns x 4 B
-constexpr int BOX_BYTES = 2048;                  // TMA box: 16 k8-rows x 32 columns, SWIZZLE_128B
+constexpr int BOX_BYTES = 2048;                  // one column group of the unit: 16 k8-rows x 32 columns, SWIZZLE_128B
 constexpr int META_SC = W_BYTES;                 // up to 4 group rows of 128 fp16 scales
 constexpr int META_ZQ = W_BYTES + 1024;          // up to 4 group rows of 128 zero nibbles
 constexpr int STAGE_STRIDE = W_BYTES + 2048;     // keeps every stage 1 KB aligned (swizzle atom)
 constexpr int PART_LD = 132;                     // attention partial: o[128], m, l, pad
 constexpr int MAX_LAYERS = 128;
+constexpr int MAX_DEPTH = 6;                     // ring stages per pipeline
+constexpr int TRACE_LAYERS = 4;
 constexpr unsigned long long WAIT_NS = 4000000000ull;   // any single wait longer than this aborts the launch
 
 enum { PH_QKV = 0, PH_ATT = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_HEAD = 5 };
 
 struct alignas(64) LayerDesc
 {
-    CUtensorMap tm[7];                 // q k v o gate up down: qweight [K/8, N] int32, box 16 x 32, SWIZZLE_128B (exl_q4_matrix::tmap_w)
-    const uint32_t* qz[7];
-    const half* sc[7];
+    CUtensorMap tw[7];                 // q k v o gate up down: exl_q4_matrix::tmap_w3 (one 8 KB unit per op)
+    CUtensorMap ts[7];                 // ::tmap_sc
+    CUtensorMap tz[7];                 // ::tmap_qz
     const half* ln1; const half* ln2;
     half* kc; half* vc;                // [heads, max_seq, 128]
 };
@@ -69,7 +72,7 @@ struct StepArgs
     int H, HQ, I;                      // hidden, attention width (heads * 128), intermediate width
     int heads, max_seq, past_len;
     int gshift;                        // log2(groupsize / 32); 30 = one group per matrix
-    int nst;                           // ring depth
+    int depth;                         // ring stages per pipeline (4 pipelines)
     int spt_max;                       // max K / 128 over the phases
     float eps;
     const half* x_in; half* x_out;     // [H] input hidden state; final hidden state (before the final norm), optional
@@ -77,7 +80,9 @@ struct StepArgs
     const half* final_norm; const half* lm_head; float* logits; int vocab;     // optional head
     float* acc_qkv; float* acc_o; float* acc_gu; float* acc_d;                 // fp32 phase accumulators in L2
     float* att_part; int att_slots;    // [heads][att_slots][PART_LD]
-    unsigned* bar;                     // grid barrier {count, generation}
+    unsigned long long* bar;           // grid barrier: monotonic arrival counter
+    int debug;                         // EXL_DS_DEBUG bitmask (bring-up experiments): 1 skip GEMV math, 2 skip attention math, 4 skip head math
+    unsigned long long* trace;         // optional [G][TRACE_LAYERS][16] globaltimer stamps of CTA thread 0 (EXL_DS_TRACE=1), else NULL
 };
 
 // ------------------------------------------------------------------------------------------------------------ helpers
@@ -96,6 +101,8 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// NOTE on parities: a waiter may be at most ONE phase ahead of the barrier (try_wait.parity cannot tell phase k from k + 2).
+// Every warp of a pipeline visits every stage of that pipeline in order, so this always holds here.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     if (mbar_try(bar, parity)) return;
@@ -113,15 +120,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t a)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar)
 {
-    uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r;
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
-__device__ __forceinline__ uint2 lds64(uint32_t a)
-{
-    uint2 r; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d)
 {
@@ -132,13 +135,13 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 // u8 (weights, 0..15) x s8 (x planes) -> s32; first MMA of a segment starts from C = 0
 __device__ __forceinline__ void imma(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void imma_z(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 
 __device__ __forceinline__ half silu_h(half x)
@@ -183,7 +186,7 @@ __device__ __forceinline__ int share_lo(long long n, int c, int G) { return (int
 // the CTA whose share contains item u (inverse of share_lo)
 __device__ __forceinline__ int cta_of(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
 
-struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; };     // tpm: tiles per matrix
+struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; };     // tpm: tiles per matrix (ATT: units per head)
 
 __device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
 {
@@ -205,53 +208,48 @@ __device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
     return p;
 }
 
-// Grid-wide barrier for the consumer threads of all CTAs (sense-reversing: count resets, generation advances; both persist
-// across launches, so graph replays need no host-side reset).
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsigned& gen, int tid)
+// Grid-wide barrier for the consumer threads of all CTAs: one monotonic 64-bit arrival counter (never reset, so graph replays
+// and back-to-back launches need no host-side state); every CTA adds 1 with release semantics and polls until the count reaches
+// the target of this barrier.  One L2 round trip to arrive, one to observe.
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long& target, unsigned nctas, int tid)
 {
     consumer_sync();
     if (tid == 0) {
-        __threadfence();
-        const unsigned want = gen + 1u;
-        const unsigned prev = atomicAdd(bar, 1u);
-        if (prev == nctas - 1u) {
-            bar[0] = 0u;
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 1), "r"(want) : "memory");
-        } else {
-            unsigned v;
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(ctr) : "memory");
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        if (v < target) {
             const unsigned long long t0 = gtime();
             unsigned i = 0;
             do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1) : "memory");
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
                 if ((++i & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
-            } while (v != want);
+            } while (v < target);
         }
-        __threadfence();
     }
-    gen += 1u;
+    target += nctas;
     consumer_sync();
 }
 
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);      // nst x STAGE_STRIDE
-    unsigned char* xs = ring + (size_t)a.nst * STAGE_STRIDE;                          // spt_max x 16 k8-rows x 16 B: quantised x planes by K stage
+    const int depth = a.depth, nst = 4 * a.depth;
+    unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);      // nst x STAGE_STRIDE: pipeline g owns stages [g * depth, (g + 1) * depth)
+    unsigned char* xs = ring + (size_t)nst * STAGE_STRIDE;                            // spt_max x 16 k8-rows x 16 B: quantised x planes by K stage
     unsigned char* segt = xs + (size_t)a.spt_max * 256;                                // spt_max x 4 x {sum x_q, x scale}
     half* xres = reinterpret_cast<half*>(segt + (size_t)a.spt_max * 32);              // [H] residual stream (fp16, as the reference keeps it)
-    float* parts = reinterpret_cast<float*>(xres + a.H);                               // [17][PART_LD] attention partials of the warps (+ the new token)
-    float* q_s = parts + 17 * PART_LD;                                                 // [128] scaled q of the current head
-    float* kn_s = q_s + TILE;                                                          // [128] newest k row (after rope)
-    float* vn_s = kn_s + TILE;                                                         // [128] newest v row
+    float* parts = reinterpret_cast<float*>(xres + a.H);                               // [2 segments][17][PART_LD] attention partials of the warps (+ the new token)
+    float* q_s = parts + 2 * 17 * PART_LD;                                             // [2][128] scaled q of the segment's head
+    float* kn_s = q_s + 2 * TILE;                                                      // [2][128] newest k row (after rope)
+    float* vn_s = kn_s + 2 * TILE;                                                     // [2][128] newest v row
     half* xh = reinterpret_cast<half*>(xs);                                            // HEAD: normalised x [H] (xs is free by then)
-    __shared__ __align__(8) unsigned long long full_bar[24], empty_bar[24];
+    __shared__ __align__(8) unsigned long long full_bar[4 * MAX_DEPTH], empty_bar[4 * MAX_DEPTH];
     __shared__ float s_red[DS_NCW];
-    __shared__ float s_rm;
+    __shared__ unsigned long long s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int nst = a.nst;
 
     if (tid == 0) {
         for (int i = 0; i < nst; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
@@ -259,17 +257,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     }
     __syncthreads();
 
-    if (warp == DS_NCW) {
-        // ============================ producer warp: the whole token's HBM stream, in schedule order ============================
-        int slot = 0; uint32_t par = 0; long long issued = 0;          // par: parity of the "empty" completion to wait for
-        const uint32_t ring_a = smem_u32(ring), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    if (warp >= DS_NCW) {
+        // ==================== producer warp of pipeline pq: every 4th stage of the token's HBM stream, in schedule order ====================
+        const int pq = warp - DS_NCW;
+        int ls = 0; uint32_t par = 0; int issued = 0;                       // ls: stage inside the pipeline's ring; par: parity of the empty completion to wait for
+        const uint32_t ring_a = smem_u32(ring) + (uint32_t)pq * depth * STAGE_STRIDE;
+        const uint32_t full0 = smem_u32(&full_bar[pq * depth]), empty0 = smem_u32(&empty_bar[pq * depth]);
+        long long jbase = 0;
         auto acquire = [&](uint32_t tx) -> uint32_t {
-            if (issued >= nst) mbar_wait(empty0 + slot * 8, par ^ 1u);
-            if (lane == 0) mbar_expect_tx(full0 + slot * 8, tx);
+            if (issued >= depth) mbar_wait(empty0 + ls * 8, par ^ 1u);
+            if (lane == 0) mbar_expect_tx(full0 + ls * 8, tx);
             __syncwarp();
-            return ring_a + (uint32_t)slot * STAGE_STRIDE;
+            return ring_a + (uint32_t)ls * STAGE_STRIDE;
         };
-        auto advance = [&]() { issued++; if (++slot == nst) { slot = 0; par ^= 1u; } };
+        auto advance = [&]() { if (issued < depth) issued++; if (++ls == depth) { ls = 0; par ^= 1u; } };
         const int ngrow = a.gshift >= 2 ? 1 : (4 >> a.gshift);          // group rows per K stage (groupsize 32: 4, 64: 2, >= 128: 1)
         #pragma unroll 1
         for (int l = 0; l < a.n_layers; l++) {
@@ -278,56 +279,54 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             for (int ph = PH_QKV; ph <= PH_DOWN; ph++) {
                 const Phase p = phase_of(a, ph);
                 const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+                const int i0 = (int)((pq - jbase) & 3);
+                jbase += u1 - u0;
                 if (ph == PH_ATT) {
                     #pragma unroll 1
-                    for (int u = u0; u < u1; u++) {
+                    for (int u = u0 + i0; u < u1; u += 4) {
                         const int h = u / p.tpm, ch = u - h * p.tpm;
                         const int pos0 = ch * 16;
                         int nv = a.past_len - pos0; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
                         const uint32_t base = acquire((uint32_t)nv * 512u);
                         if (nv > 0) {
                             const size_t off = ((size_t)h * a.max_seq + pos0) * TILE;
-                            if (lane == 0) bulk_g2s(base, L->kc + off, (uint32_t)nv * 256u, full0 + slot * 8);
-                            if (lane == 1) bulk_g2s(base + 4096, L->vc + off, (uint32_t)nv * 256u, full0 + slot * 8);
+                            if (lane == 0) bulk_g2s(base, L->kc + off, (uint32_t)nv * 256u, full0 + ls * 8);
+                            if (lane == 1) bulk_g2s(base + 4096, L->vc + off, (uint32_t)nv * 256u, full0 + ls * 8);
                         }
                         advance();
                     }
                     continue;
                 }
-                if (u1 <= u0) continue;
-                int tile = u0 / p.spt, s = u0 - tile * p.spt;
+                if (u0 + i0 >= u1) continue;
+                int tile = (u0 + i0) / p.spt, s = (u0 + i0) - tile * p.spt;
+                int mi = tile / p.tpm, ct = tile - mi * p.tpm;
                 #pragma unroll 1
-                for (int u = u0; u < u1; u++) {
-                    const int mi = tile / p.tpm, col0 = (tile - mi * p.tpm) * TILE;
+                for (int u = u0 + i0; u < u1; u += 4) {
                     const int m = p.mat0 + mi;
                     const uint32_t base = acquire((uint32_t)W_BYTES + (uint32_t)ngrow * 320u);
-                    const uint32_t fb = full0 + slot * 8;
-                    if (lane < 4) tma_load_2d(base + lane * BOX_BYTES, &L->tm[m], col0 + lane * 32, s * 16, fb);
-                    else if (lane < 4 + ngrow) {
-                        const int r = lane - 4;
-                        const int grp = a.gshift >= 2 ? ((s * 4) >> a.gshift) : (s * ngrow + r);
-                        bulk_g2s(base + META_SC + r * 256, L->sc[m] + (size_t)grp * p.N + col0, 256u, fb);
-                    } else if (lane < 4 + 2 * ngrow) {
-                        const int r = lane - 4 - ngrow;
-                        const int grp = a.gshift >= 2 ? ((s * 4) >> a.gshift) : (s * ngrow + r);
-                        bulk_g2s(base + META_ZQ + r * 64, L->qz[m] + (size_t)grp * (p.N >> 3) + (col0 >> 3), 64u, fb);
-                    }
+                    const uint32_t fb = full0 + ls * 8;
+                    const int grow = a.gshift >= 2 ? ((s * 4) >> a.gshift) : s * ngrow;
+                    if (lane == 0) tma_load_3d(base, &L->tw[m], 0, s * 16, ct * 4, fb);
+                    else if (lane == 1) tma_load_2d(base + META_SC, &L->ts[m], ct * TILE, grow, fb);
+                    else if (lane == 2) tma_load_2d(base + META_ZQ, &L->tz[m], ct * 16, grow, fb);
                     advance();
-                    if (++s == p.spt) { s = 0; tile++; }
+                    s += 4;
+                    while (s >= p.spt) { s -= p.spt; if (++ct == p.tpm) { ct = 0; mi++; } }
                 }
             }
         }
         {
             const Phase p = phase_of(a, PH_HEAD);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const int i0 = (int)((pq - jbase) & 3);
             const long long total = (long long)a.vocab * a.H * 2;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.lm_head);
             #pragma unroll 1
-            for (int u = u0; u < u1; u++) {
+            for (int u = u0 + i0; u < u1; u += 4) {
                 const long long off = (long long)u * W_BYTES;
                 const uint32_t bytes = (uint32_t)((total - off) < W_BYTES ? (total - off) : W_BYTES);
                 const uint32_t base = acquire(bytes);
-                if (lane == 0) bulk_g2s(base, src + off, bytes, full0 + slot * 8);
+                if (lane == 0) bulk_g2s(base, src + off, bytes, full0 + ls * 8);
                 advance();
             }
         }
@@ -335,18 +334,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     }
 
     // ======================================================= consumer warps =======================================================
-    const int wn = warp & 3, wk = warp >> 2;
+    const int wn = warp & 3, wk = warp >> 2;             // wk: pipeline; wn: 32-column quarter of the tile (ATT: 4 positions, HEAD: 2 chunks)
     const int g = lane >> 2, t = lane & 3;
     const int pg = (g >> 1) | ((g & 1) << 2);            // column chunk of this lane (bank-conflict-free against the 128B swizzle)
     const int lane_col = wn * 32 + 4 * pg;
-    const uint32_t ring_a = smem_u32(ring), xs_a = smem_u32(xs), seg_a = smem_u32(segt);
-    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-    long long jbase = 0;                                 // ring position of the next stage this CTA consumes (same count as the producer)
-    unsigned gen;
-    if (tid == 0) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar + 1) : "memory"); s_red[0] = __uint_as_float(v); }
+    const uint32_t ring_a = smem_u32(ring) + (uint32_t)wk * depth * STAGE_STRIDE;
+    const uint32_t full0 = smem_u32(&full_bar[wk * depth]), empty0 = smem_u32(&empty_bar[wk * depth]);
+    int ls = 0; uint32_t par = 0;                        // this pipeline's ring position (every warp of the pipeline visits every stage)
+    auto stamp = [&](int l, int ev) { if (a.trace && tid == 0 && l < TRACE_LAYERS) a.trace[((size_t)cta * TRACE_LAYERS + l) * 16 + ev] = gtime(); };
+    long long jbase = 0;                                 // stages this CTA has been through (same count as the producers)
+    if (tid == 0) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+        s_base = v - v % (unsigned long long)G;          // at most G - 1 CTAs of THIS launch can have arrived already
+    }
     consumer_sync();
-    gen = __float_as_uint(s_red[0]);
-    consumer_sync();
+    unsigned long long target = s_base + (unsigned long long)G;
 
     auto zero_share = [&](float* buf, int n) {            // this CTA's share of a float buffer (n % 4 == 0)
         const int lo = share_lo(n >> 2, cta, G), hi = share_lo(n >> 2, cta + 1, G);
@@ -358,10 +361,27 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     if (a.logits) zero_share(a.logits, a.vocab);
     for (int i = tid; i < a.H / 8; i += DS_CONSUMERS)
         reinterpret_cast<uint4*>(xres)[i] = __ldg(reinterpret_cast<const uint4*>(a.x_in) + i);
-    grid_barrier(a.bar, (unsigned)G, gen, tid);
+
+    const int rpg = a.gshift >= 2 ? 16 : (4 << a.gshift);          // k8-rows per quantisation segment (a segment never spans stages)
+
+    // Norm weights of the rows this thread will quantise in the NEXT norm phase: constants, so they are fetched BEFORE the grid
+    // barrier and the phase prologue is left with one L2 round trip (the accumulator) instead of two.
+    uint4 wpre[2];
+    auto preload_norm = [&](const half* nw, const Phase& p) {
+        const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+        const int n = min(u1 - u0, p.spt), s0 = u1 > u0 ? u0 % p.spt : 0;
+        #pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int r = it * DS_CONSUMERS + tid;
+            int s = s0 + (r >> 4); if (s >= p.spt) s -= p.spt;
+            wpre[it] = r < n * 16 ? __ldg(reinterpret_cast<const uint4*>(nw) + (s * 16 + (r & 15))) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    preload_norm(a.layers[0].ln1, phase_of(a, PH_QKV));
+    grid_barrier(a.bar, target, (unsigned)G, tid);
 
     // ---- residual add (fp16(x + fp32 delta), the rounding point of q4_matmul's no_zero epilogue) + row factor of the RMS norm ----
-    auto residual_and_norm = [&](const float* delta) {
+    auto residual_and_norm = [&](const float* delta) -> float {
         float ss = 0.f;
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
             uint4 xv = reinterpret_cast<uint4*>(xres)[i];
@@ -381,26 +401,23 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) s_red[warp] = ss;
-        consumer_sync();
-        if (tid == 0) {
-            float tot = 0.f;
-            #pragma unroll
-            for (int w = 0; w < DS_NCW; w++) tot += s_red[w];
-            s_rm = __half2float(__float2half_rn(rsqrtf(tot / (float)a.H + a.eps)));       // rms_norm.cu:113-116
-        }
-        consumer_sync();
+        consumer_sync();                                      // also publishes the updated xres
+        float tot = 0.f;
+        #pragma unroll
+        for (int w = 0; w < DS_NCW; w++) tot += s_red[w];     // same order in every thread
+        return __half2float(__float2half_rn(rsqrtf(tot / (float)a.H + a.eps)));       // rms_norm.cu:113-116
     };
 
-    // ---- quantise the K stages [s0, s0 + n) (cyclic mod spt) of the phase input into xs / segt; `get(k8)` yields 8 fp16 values ----
-    const int rpg = a.gshift >= 2 ? 16 : (4 << a.gshift);          // k8-rows per quantisation segment (a segment never spans stages)
+    // ---- quantise the K stages [s0, s0 + n) (cyclic mod spt) of the phase input into xs / segt; `get(k8, it)` yields 8 fp16 values ----
     auto stage_x = [&](int s0, int n, int spt, auto get) {
         const int nrows = n * 16;
-        for (int base = 0; base < nrows; base += DS_CONSUMERS) {
+        int it = 0;
+        for (int base = 0; base < nrows; base += DS_CONSUMERS, it++) {
             const int r = base + tid;
             const bool act = r < nrows;
             int s = s0 + (r >> 4); if (s >= spt) s -= spt;
             const int rr = r & 15;
-            const uint4 hv = act ? get(s * 16 + rr) : make_uint4(0, 0, 0, 0);
+            const uint4 hv = act ? get(s * 16 + rr, it) : make_uint4(0, 0, 0, 0);
             float mx = row_absmax(hv);
             for (int o = rpg >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             uint4 q;
@@ -413,15 +430,23 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
         }
     };
+    auto norm_get = [&](const half* nw, float rm) {
+        return [=, &wpre](int k8, int it) -> uint4 {
+            uint4 xv = reinterpret_cast<const uint4*>(xres)[k8];
+            const uint4 wv = it < 2 ? wpre[it] : __ldg(reinterpret_cast<const uint4*>(nw) + k8);
+            const half2 rm2 = __float2half2_rn(rm);
+            half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
+            #pragma unroll
+            for (int i = 0; i < 4; i++) h[i] = __hmul2(__hmul2(h[i], rm2), w2[i]);      // rms_norm.cu:118-131
+            return xv;
+        };
+    };
 
-    // ---- GEMV phase body: this warp's stages of the CTA's unit range ----
+    // ---- GEMV phase body: this pipeline's stages of the CTA's unit range, this warp's 32 columns ----
     auto gemv = [&](const Phase& p, int u0, int u1) {
-        const int n = u1 - u0;
-        int i = (int)((wk - jbase) & 3);                     // stage j of the CTA goes to k-warp group j & 3
-        if (i >= n) return;
-        long long j = jbase + i;
-        int slot = (int)(j % nst); uint32_t par = (uint32_t)((j / nst) & 1);
-        int tile = (u0 + i) / p.spt, s = (u0 + i) - tile * p.spt;
+        int u = u0 + (int)((wk - jbase) & 3);                // stage j of the CTA goes to pipeline j & 3
+        if (u >= u1) return;
+        int tile = u / p.spt, s = u - tile * p.spt;
         int cur_tile = tile;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         int ia[8];
@@ -433,58 +458,65 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
             acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         };
-        for (; i < n; i += 4) {
+        for (; u < u1; u += 4) {
             if (tile != cur_tile) { flush_tile(); cur_tile = tile; }
-            mbar_wait(full0 + slot * 8, par);
-            const uint32_t sb = ring_a + (uint32_t)slot * STAGE_STRIDE;
-            const uint32_t xrow = xs_a + (uint32_t)s * 256u + (uint32_t)t * 16u + (uint32_t)(g & 1) * 8u;
-            int (&aA)[4] = *reinterpret_cast<int (*)[4]>(&ia[0]);
-            int (&aB)[4] = *reinterpret_cast<int (*)[4]>(&ia[4]);
-            #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int r = u * 4 + t;                    // k8-row of this lane inside the stage
-                const uint4 w = lds128(sb + wn * BOX_BYTES + r * 128 + ((pg ^ (r & 7)) << 4));
-                uint2 xv = lds64(xrow + u * 64);
-                if (g >= 2) xv = make_uint2(0u, 0u);        // B column g: 0 = high-byte plane, 1 = low-byte plane, others unused
-                const uint32_t M4 = 0x0f0f0f0fu;
-                const uint32_t lo0 = w.x & M4, hi0 = (w.x >> 4) & M4, lo1 = w.y & M4, hi1 = (w.y >> 4) & M4;
-                const uint32_t lo2 = w.z & M4, hi2 = (w.z >> 4) & M4, lo3 = w.w & M4, hi3 = (w.w >> 4) & M4;
-                if ((u & (upseg - 1)) == 0) {
-                    imma_z(aA, lo0, lo1, hi0, hi1, xv.x, xv.y);
-                    imma_z(aB, lo2, lo3, hi2, hi3, xv.x, xv.y);
-                } else {
-                    imma(aA, lo0, lo1, hi0, hi1, xv.x, xv.y);
-                    imma(aB, lo2, lo3, hi2, hi3, xv.x, xv.y);
+            mbar_wait(full0 + ls * 8, par);
+            if (!(a.debug & 1)) {
+                const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
+                const unsigned char* xrow = xs + (size_t)s * 256 + t * 16 + (g & 1) * 8;
+                uint4 w[4]; uint2 xv[4];
+                #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int r = q * 4 + t;                // k8-row of this lane inside the stage
+                    w[q] = *reinterpret_cast<const uint4*>(sb + wn * BOX_BYTES + r * 128 + ((pg ^ (r & 7)) << 4));
+                    xv[q] = *reinterpret_cast<const uint2*>(xrow + q * 64);
+                    if (g >= 2) xv[q] = make_uint2(0u, 0u);    // B column g: 0 = high-byte plane, 1 = low-byte plane, others unused
                 }
-                if (((u + 1) & (upseg - 1)) == 0) {
-                    // segment complete: acc += scale * sx * (256 * sum a q + sum b q - zp * sum x_q)
-                    const int seg = u / upseg;
-                    const int row = a.gshift >= 2 ? 0 : seg;
-                    const uint2 sc2 = lds64(sb + META_SC + row * 256 + lane_col * 2);
-                    const uint32_t zw = lds32(sb + META_ZQ + row * 64 + (lane_col >> 3) * 4);
-                    const uint2 sg = lds64(seg_a + (uint32_t)s * 32u + (uint32_t)seg * 8u);
-                    const int sxq = (int)sg.x; const float sx = __uint_as_float(sg.y);
-                    const half2 s01 = *reinterpret_cast<const half2*>(&sc2.x), s23 = *reinterpret_cast<const half2*>(&sc2.y);
-                    const float cs4[4] = {__low2float(s01), __high2float(s01), __low2float(s23), __high2float(s23)};
-                    const uint32_t z4 = zw >> ((lane_col & 4) * 4);
-                    #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        // lane t == 0: D(row g / g+8, col 0 = plane a, col 1 = plane b); column c of this lane = MMA (c >> 1), row half (c & 1)
-                        const int jj = (c >> 1) * 4 + (c & 1) * 2;
-                        const int zp = (int)((z4 >> (4 * c)) & 0xfu) + 1;
-                        const int val = ia[jj] * 256 + ia[jj + 1] - zp * sxq;
-                        acc[c] = fmaf(cs4[c] * sx, (float)val, acc[c]);
+                int (&aA)[4] = *reinterpret_cast<int (*)[4]>(&ia[0]);
+                int (&aB)[4] = *reinterpret_cast<int (*)[4]>(&ia[4]);
+                #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t M4 = 0x0f0f0f0fu;
+                    const uint32_t lo0 = w[q].x & M4, hi0 = (w[q].x >> 4) & M4, lo1 = w[q].y & M4, hi1 = (w[q].y >> 4) & M4;
+                    const uint32_t lo2 = w[q].z & M4, hi2 = (w[q].z >> 4) & M4, lo3 = w[q].w & M4, hi3 = (w[q].w >> 4) & M4;
+                    if ((q & (upseg - 1)) == 0) {
+                        imma_z(aA, lo0, lo1, hi0, hi1, xv[q].x, xv[q].y);
+                        imma_z(aB, lo2, lo3, hi2, hi3, xv[q].x, xv[q].y);
+                    } else {
+                        imma(aA, lo0, lo1, hi0, hi1, xv[q].x, xv[q].y);
+                        imma(aB, lo2, lo3, hi2, hi3, xv[q].x, xv[q].y);
+                    }
+                    if (((q + 1) & (upseg - 1)) == 0) {
+                        // segment complete: acc += scale * sx * (256 * sum a q + sum b q - zp * sum x_q)
+                        const int seg = q / upseg;
+                        const int row = a.gshift >= 2 ? 0 : seg;
+                        const uint2 sc2 = *reinterpret_cast<const uint2*>(sb + META_SC + row * 256 + lane_col * 2);
+                        const uint32_t zw = *reinterpret_cast<const uint32_t*>(sb + META_ZQ + row * 64 + (lane_col >> 3) * 4);
+                        const uint2 sg = *reinterpret_cast<const uint2*>(segt + (size_t)s * 32 + seg * 8);
+                        const int sxq = (int)sg.x; const float sx = __uint_as_float(sg.y);
+                        const half2 s01 = *reinterpret_cast<const half2*>(&sc2.x), s23 = *reinterpret_cast<const half2*>(&sc2.y);
+                        const float cs4[4] = {__low2float(s01), __high2float(s01), __low2float(s23), __high2float(s23)};
+                        const uint32_t z4 = zw >> ((lane_col & 4) * 4);
+                        #pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            // lane t == 0: D(row g / g+8, col 0 = plane a, col 1 = plane b); column c of this lane = MMA (c >> 1), row half (c & 1)
+                            const int jj = (c >> 1) * 4 + (c & 1) * 2;
+                            const int zp = (int)((z4 >> (4 * c)) & 0xfu) + 1;
+                            const int val = ia[jj] * 256 + ia[jj + 1] - zp * sxq;
+                            acc[c] = fmaf(cs4[c] * sx, (float)val, acc[c]);
+                        }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + slot * 8);
-            slot += 4; if (slot >= nst) { slot -= nst; par ^= 1u; }
+            if (lane == 0) mbar_arrive(empty0 + ls * 8);
+            if (++ls == depth) { ls = 0; par ^= 1u; }
             s += 4; while (s >= p.spt) { s -= p.spt; tile++; }
         }
         flush_tile();
     };
 
+    float rm = 0.f;
     #pragma unroll 1
     for (int l = 0; l < a.n_layers; l++) {
         const LayerDesc* L = a.layers + l;
@@ -492,25 +524,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_QKV);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            stamp(l, 0);
             if (l > 0) zero_share(a.acc_gu, 2 * a.I);
-            residual_and_norm(l > 0 ? a.acc_d : nullptr);
-            if (u1 > u0) {
-                const half* nw = L->ln1;
-                const half2 rm2 = __float2half2_rn(s_rm);
-                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
-                    uint4 xv = reinterpret_cast<const uint4*>(xres)[k8];
-                    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(nw) + k8);
-                    half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
-                    #pragma unroll
-                    for (int i = 0; i < 4; i++) h[i] = __hmul2(__hmul2(h[i], rm2), w2[i]);      // rms_norm.cu:118-131
-                    return xv;
-                });
-            }
+            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr);
+            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(L->ln1, rm));
             consumer_sync();
+            stamp(l, 1);
             gemv(p, u0, u1);
             jbase += u1 - u0;
+            stamp(l, 2);
         }
-        grid_barrier(a.bar, (unsigned)G, gen, tid);
+        grid_barrier(a.bar, target, (unsigned)G, tid);
+        stamp(l, 3);
 
         // ======================================================== ATT ========================================================
         {
@@ -520,123 +545,145 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int nph = p.tpm;
             const float scale = rsqrtf((float)TILE);
             const int l16 = lane & 15, sub = lane >> 4;
-            for (int h = (u1 > u0 ? u0 / nph : 0); u1 > u0 && h * nph < u1; h++) {
-                const int ua = max(u0, h * nph), ub = min(u1, (h + 1) * nph);
-                const bool owner = ub == (h + 1) * nph;            // this CTA holds the head's last chunk: it also takes the new token
-                consumer_sync();                                   // previous segment's parts / q_s consumed
-                if (tid < TILE) {
-                    // q (and k) of this head: fp16 projection result, rope in fp16 with the reference's instruction order (rope.cu:48-67)
-                    const half* sr = a.sin + (size_t)a.past_len * TILE;
-                    const half* cr = a.cos + (size_t)a.past_len * TILE;
-                    const float* aq = a.acc_qkv + (size_t)h * TILE;
-                    const half qv = __float2half_rn(__ldcg(aq + tid)), qo = __float2half_rn(__ldcg(aq + (tid ^ 64)));
-                    const half sn = tid < 64 ? __hneg(sr[tid]) : sr[tid];
-                    q_s[tid] = __half2float(__hfma(qv, cr[tid], __hmul(qo, sn))) * scale;
-                    if (owner) {
-                        const float* ak = a.acc_qkv + a.HQ + (size_t)h * TILE;
-                        const half kv = __float2half_rn(__ldcg(ak + tid)), ko = __float2half_rn(__ldcg(ak + (tid ^ 64)));
-                        const half kr = __hfma(kv, cr[tid], __hmul(ko, sn));
-                        const half vv = __float2half_rn(__ldcg(a.acc_qkv + 2 * a.HQ + (size_t)h * TILE + tid));
-                        kn_s[tid] = __half2float(kr); vn_s[tid] = __half2float(vv);
-                        const size_t off = ((size_t)h * a.max_seq + a.past_len) * TILE + tid;      // cache layout q4_attn.cu:32-51
-                        L->kc[off] = kr; L->vc[off] = vv;
-                    }
-                }
-                consumer_sync();
-                float qf[8];
-                #pragma unroll
-                for (int j = 0; j < 8; j++) qf[j] = q_s[l16 * 8 + j];
-                float m = -INFINITY, lsum = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-                // stages of this segment: local indices [ua - u0, ub - u0); stage j of the CTA goes to warp j & 15
-                int i = (ua - u0) + (int)((warp - (jbase + (ua - u0))) & 15);
-                if (i < ub - u0) {
-                    long long j = jbase + i;
-                    int slot = (int)(j % nst); uint32_t par = (uint32_t)((j / nst) & 1);
-                    for (; i < ub - u0; i += 16) {
-                        const int ch = (u0 + i) - h * nph;
-                        int nv = a.past_len - ch * 16; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
-                        mbar_wait(full0 + slot * 8, par);
-                        const uint32_t sb = ring_a + (uint32_t)slot * STAGE_STRIDE;
-                        float sc8[8];
-                        float smax = -INFINITY;
-                        #pragma unroll
-                        for (int it = 0; it < 8; it++) {
-                            const int pp = it * 2 + sub;
-                            const uint4 kv = lds128(sb + pp * 256 + l16 * 16);
-                            const half2* hh = reinterpret_cast<const half2*>(&kv);
-                            float d = 0.f;
-                            #pragma unroll
-                            for (int q = 0; q < 4; q++) { const float2 f = __half22float2(hh[q]); d = fmaf(f.x, qf[2 * q], d); d = fmaf(f.y, qf[2 * q + 1], d); }
-                            d += __shfl_xor_sync(0xffffffffu, d, 8); d += __shfl_xor_sync(0xffffffffu, d, 4);
-                            d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 1);
-                            sc8[it] = pp < nv ? d : -INFINITY;
-                            smax = fmaxf(smax, sc8[it]);
-                        }
-                        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 16));
-                        if (nv > 0) {
-                            const float mnew = fmaxf(m, smax);
-                            const float alpha = __expf(m - mnew);
-                            float psum = 0.f;
-                            #pragma unroll
-                            for (int it = 0; it < 8; it++) { sc8[it] = __expf(sc8[it] - mnew); psum += sc8[it]; }
-                            psum += __shfl_xor_sync(0xffffffffu, psum, 16);
-                            lsum = lsum * alpha + psum;
-                            #pragma unroll
-                            for (int c = 0; c < 4; c++) o[c] *= alpha;
-                            m = mnew;
-                            #pragma unroll
-                            for (int pp = 0; pp < 16; pp++) {
-                                const float w = __shfl_sync(0xffffffffu, sc8[pp >> 1], (pp & 1) * 16);
-                                if (pp < nv) {
-                                    const uint2 vv = lds64(sb + 4096 + pp * 256 + lane * 8);
-                                    const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&vv.x));
-                                    const float2 f1 = __half22float2(*reinterpret_cast<const half2*>(&vv.y));
-                                    o[0] = fmaf(w, f0.x, o[0]); o[1] = fmaf(w, f0.y, o[1]); o[2] = fmaf(w, f1.x, o[2]); o[3] = fmaf(w, f1.y, o[3]);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (lane < 4) mbar_arrive(empty0 + slot * 8);
-                        slot += 16; while (slot >= nst) { slot -= nst; par ^= 1u; }
-                    }
-                }
-                {
-                    float* pw = parts + warp * PART_LD;
-                    *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                    if (lane == 0) { pw[128] = m; pw[129] = lsum; }
-                }
-                if (owner && warp == 0) {
-                    // the new token itself: score q . k_new, weight 1 in its own partial
-                    float d = 0.f;
-                    #pragma unroll
-                    for (int c = 0; c < 4; c++) d = fmaf(q_s[lane * 4 + c], kn_s[lane * 4 + c], d);
-                    #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-                    float* pw = parts + 16 * PART_LD;
-                    *reinterpret_cast<float4*>(pw + lane * 4) = *reinterpret_cast<const float4*>(vn_s + lane * 4);
-                    if (lane == 0) { pw[128] = d; pw[129] = 1.0f; }
-                }
-                consumer_sync();
-                if (tid < TILE) {
-                    const int np = owner ? 17 : 16;
-                    float M = -INFINITY;
-                    for (int w = 0; w < np; w++) M = fmaxf(M, parts[w * PART_LD + 128]);
-                    float Lt = 0.f, ov = 0.f;
-                    for (int w = 0; w < np; w++) {
-                        const float mw = parts[w * PART_LD + 128];
-                        const float wgt = mw == -INFINITY ? 0.f : __expf(mw - M);
-                        Lt = fmaf(parts[w * PART_LD + 129], wgt, Lt);
-                        ov = fmaf(parts[w * PART_LD + tid], wgt, ov);
-                    }
-                    const int slot_id = cta - cta_of((long long)h * nph, p.U, G);
-                    float* dst = a.att_part + ((size_t)h * a.att_slots + slot_id) * PART_LD;
-                    dst[tid] = ov;
-                    if (tid == 0) { dst[128] = M; dst[129] = Lt; }
+            const int h0 = u1 > u0 ? u0 / nph : 0;
+            const int nseg = u1 > u0 ? (u1 - 1) / nph - h0 + 1 : 0;            // <= 2 (heads <= grid, checked on the host)
+            // every segment's q (and the new k / v rows where this CTA owns the head's last chunk): one L2 round trip
+            if (tid < nseg * TILE) {
+                const int sg = tid >> 7, d = tid & 127, h = h0 + sg;
+                const bool owner = min(u1, (h + 1) * nph) == (h + 1) * nph;
+                // fp16 projection result, rope in fp16 with the reference's instruction order (rope.cu:48-67)
+                const half* sr = a.sin + (size_t)a.past_len * TILE;
+                const half* cr = a.cos + (size_t)a.past_len * TILE;
+                const float* aq = a.acc_qkv + (size_t)h * TILE;
+                const half qv = __float2half_rn(__ldcg(aq + d)), qo = __float2half_rn(__ldcg(aq + (d ^ 64)));
+                const half sn = d < 64 ? __hneg(sr[d]) : sr[d];
+                q_s[sg * TILE + d] = __half2float(__hfma(qv, cr[d], __hmul(qo, sn))) * scale;
+                if (owner) {
+                    const float* ak = a.acc_qkv + a.HQ + (size_t)h * TILE;
+                    const half kv = __float2half_rn(__ldcg(ak + d)), ko = __float2half_rn(__ldcg(ak + (d ^ 64)));
+                    const half kr = __hfma(kv, cr[d], __hmul(ko, sn));
+                    const half vv = __float2half_rn(__ldcg(a.acc_qkv + 2 * a.HQ + (size_t)h * TILE + d));
+                    kn_s[sg * TILE + d] = __half2float(kr); vn_s[sg * TILE + d] = __half2float(vv);
+                    const size_t off = ((size_t)h * a.max_seq + a.past_len) * TILE + d;      // cache layout q4_attn.cu:32-51
+                    L->kc[off] = kr; L->vc[off] = vv;
                 }
             }
+            consumer_sync();
+            {
+                // this pipeline's stages, in order; the 4 warps of the pipeline take 4 positions of each 16-position chunk
+                float qf[8];
+                float m = -INFINITY, lsum = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+                int cur = -1;                                  // segment the running (m, l, o) belongs to
+                auto put_part = [&]() {
+                    float* pw = parts + (cur * 17 + warp) * PART_LD;
+                    *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (lane == 0) { pw[128] = m; pw[129] = lsum; }
+                };
+                for (int u = u0 + (int)((wk - jbase) & 3); u < u1; u += 4) {
+                    const int h = u / nph, sg = h - h0, ch = u - h * nph;
+                    if (sg != cur) {
+                        if (cur >= 0) put_part();
+                        cur = sg; m = -INFINITY; lsum = 0.f; o[0] = o[1] = o[2] = o[3] = 0.f;
+                        #pragma unroll
+                        for (int j = 0; j < 8; j++) qf[j] = q_s[sg * TILE + l16 * 8 + j];
+                    }
+                    int nv = a.past_len - ch * 16; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
+                    mbar_wait(full0 + ls * 8, par);
+                    const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
+                    float sc2[2];
+                    float smax = -INFINITY;
+                    #pragma unroll
+                    for (int it = 0; it < 2; it++) {
+                        const int pp = wn * 4 + it * 2 + sub;
+                        const uint4 kv = *reinterpret_cast<const uint4*>(sb + pp * 256 + l16 * 16);
+                        const half2* hh = reinterpret_cast<const half2*>(&kv);
+                        float d = 0.f;
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) { const float2 f = __half22float2(hh[q]); d = fmaf(f.x, qf[2 * q], d); d = fmaf(f.y, qf[2 * q + 1], d); }
+                        d += __shfl_xor_sync(0xffffffffu, d, 8); d += __shfl_xor_sync(0xffffffffu, d, 4);
+                        d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 1);
+                        sc2[it] = pp < nv ? d : -INFINITY;
+                        smax = fmaxf(smax, sc2[it]);
+                    }
+                    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 16));
+                    if (smax > -INFINITY && !(a.debug & 2)) {           // this warp has at least one valid position in the chunk
+                        const float mnew = fmaxf(m, smax);
+                        const float alpha = __expf(m - mnew);
+                        sc2[0] = __expf(sc2[0] - mnew); sc2[1] = __expf(sc2[1] - mnew);
+                        float psum = sc2[0] + sc2[1];
+                        psum += __shfl_xor_sync(0xffffffffu, psum, 16);
+                        lsum = lsum * alpha + psum;
+                        #pragma unroll
+                        for (int c = 0; c < 4; c++) o[c] *= alpha;
+                        m = mnew;
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int pp = wn * 4 + q;
+                            const float wgt = __shfl_sync(0xffffffffu, sc2[q >> 1], (q & 1) * 16);
+                            if (pp < nv) {
+                                const uint2 vv = *reinterpret_cast<const uint2*>(sb + 4096 + pp * 256 + lane * 8);
+                                const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&vv.x));
+                                const float2 f1 = __half22float2(*reinterpret_cast<const half2*>(&vv.y));
+                                o[0] = fmaf(wgt, f0.x, o[0]); o[1] = fmaf(wgt, f0.y, o[1]); o[2] = fmaf(wgt, f1.x, o[2]); o[3] = fmaf(wgt, f1.y, o[3]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + ls * 8);
+                    if (++ls == depth) { ls = 0; par ^= 1u; }
+                }
+                if (cur >= 0) put_part();
+                // segments this warp saw no stage of: an empty partial
+                for (int sg = 0; sg < nseg; sg++) {
+                    const int first = max(u0, (h0 + sg) * nph), last = min(u1, (h0 + sg + 1) * nph);
+                    // did this pipeline get a stage of segment sg?  stages of the segment: local indices [first - u0, last - u0)
+                    const int i0 = (first - u0) + (int)((wk - (jbase + (first - u0))) & 3);
+                    if (i0 >= last - u0) {
+                        float* pw = parts + (sg * 17 + warp) * PART_LD;
+                        *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lane == 0) { pw[128] = -INFINITY; pw[129] = 0.f; }
+                    }
+                }
+                if (warp < nseg) {
+                    // the new token itself (segments whose last chunk this CTA holds): score q . k_new, weight 1 in its own partial
+                    const int sg = warp, h = h0 + sg;
+                    if (min(u1, (h + 1) * nph) == (h + 1) * nph) {
+                        float d = 0.f;
+                        #pragma unroll
+                        for (int c = 0; c < 4; c++) d = fmaf(q_s[sg * TILE + lane * 4 + c], kn_s[sg * TILE + lane * 4 + c], d);
+                        #pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                        float* pw = parts + (sg * 17 + 16) * PART_LD;
+                        *reinterpret_cast<float4*>(pw + lane * 4) = *reinterpret_cast<const float4*>(vn_s + sg * TILE + lane * 4);
+                        if (lane == 0) { pw[128] = d; pw[129] = 1.0f; }
+                    }
+                }
+            }
+            consumer_sync();
+            if (tid < nseg * TILE) {
+                const int sg = tid >> 7, d = tid & 127, h = h0 + sg;
+                const bool owner = min(u1, (h + 1) * nph) == (h + 1) * nph;
+                const float* pp = parts + sg * 17 * PART_LD;
+                const int np = owner ? 17 : 16;
+                float M = -INFINITY;
+                for (int w = 0; w < np; w++) M = fmaxf(M, pp[w * PART_LD + 128]);
+                float Lt = 0.f, ov = 0.f;
+                for (int w = 0; w < np; w++) {
+                    const float mw = pp[w * PART_LD + 128];
+                    const float wgt = mw == -INFINITY ? 0.f : __expf(mw - M);
+                    Lt = fmaf(pp[w * PART_LD + 129], wgt, Lt);
+                    ov = fmaf(pp[w * PART_LD + d], wgt, ov);
+                }
+                const int slot_id = cta - cta_of((long long)h * nph, p.U, G);
+                float* dst = a.att_part + ((size_t)h * a.att_slots + slot_id) * PART_LD;
+                dst[d] = ov;
+                if (d == 0) { dst[128] = M; dst[129] = Lt; }
+            }
             jbase += u1 - u0;
+            stamp(l, 4);
         }
-        grid_barrier(a.bar, (unsigned)G, gen, tid);
+        grid_barrier(a.bar, target, (unsigned)G, tid);
+        stamp(l, 5);
 
         // ========================================================= O =========================================================
         {
@@ -645,21 +692,38 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             zero_share(a.acc_qkv, 3 * a.HQ);
             if (u1 > u0) {
                 const Phase pa = phase_of(a, PH_ATT);
-                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
-                    // softmax-combine of the CTA partials of head k8 / 16 (model.py:402-409), 8 dims per thread, fp16 result
+                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
+                    // softmax-combine of the CTA partials of head k8 / 16 (model.py:402-409), 8 dims per thread, fp16 result.
+                    // All loads of up to 8 partials are issued together: one L2 round trip.
                     const int h = k8 >> 4, d0 = (k8 & 15) * 8;
                     const int c_lo = cta_of((long long)h * pa.tpm, pa.U, G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, G);
+                    const int ns = c_hi - c_lo + 1;
                     const float* src = a.att_part + (size_t)h * a.att_slots * PART_LD;
-                    float M = -INFINITY;
-                    for (int sl = 0; sl <= c_hi - c_lo; sl++) M = fmaxf(M, __ldcg(src + sl * PART_LD + 128));
-                    float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    for (int sl = 0; sl <= c_hi - c_lo; sl++) {
-                        const float mw = __ldcg(src + sl * PART_LD + 128);
-                        const float wgt = mw == -INFINITY ? 0.f : __expf(mw - M);
-                        Lt = fmaf(__ldcg(src + sl * PART_LD + 129), wgt, Lt);
-                        const float4 o0 = ldcg4(src + sl * PART_LD + d0), o1 = ldcg4(src + sl * PART_LD + d0 + 4);
-                        ov[0] = fmaf(o0.x, wgt, ov[0]); ov[1] = fmaf(o0.y, wgt, ov[1]); ov[2] = fmaf(o0.z, wgt, ov[2]); ov[3] = fmaf(o0.w, wgt, ov[3]);
-                        ov[4] = fmaf(o1.x, wgt, ov[4]); ov[5] = fmaf(o1.y, wgt, ov[5]); ov[6] = fmaf(o1.z, wgt, ov[6]); ov[7] = fmaf(o1.w, wgt, ov[7]);
+                    float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY;
+                    for (int b = 0; b < ns; b += 4) {
+                        float mw[4], lw[4]; float4 o0[4], o1[4];
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const bool ok = b + q < ns;
+                            const float* sp = src + (size_t)(ok ? b + q : 0) * PART_LD;
+                            mw[q] = ok ? __ldcg(sp + 128) : -INFINITY; lw[q] = __ldcg(sp + 129);
+                            o0[q] = ldcg4(sp + d0); o1[q] = ldcg4(sp + d0 + 4);
+                        }
+                        float Mn = M;
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) Mn = fmaxf(Mn, mw[q]);
+                        const float resc = M == -INFINITY ? 0.f : __expf(M - Mn);
+                        Lt *= resc;
+                        #pragma unroll
+                        for (int i = 0; i < 8; i++) ov[i] *= resc;
+                        M = Mn;
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float wgt = mw[q] == -INFINITY ? 0.f : __expf(mw[q] - M);
+                            Lt = fmaf(lw[q], wgt, Lt);
+                            ov[0] = fmaf(o0[q].x, wgt, ov[0]); ov[1] = fmaf(o0[q].y, wgt, ov[1]); ov[2] = fmaf(o0[q].z, wgt, ov[2]); ov[3] = fmaf(o0[q].w, wgt, ov[3]);
+                            ov[4] = fmaf(o1[q].x, wgt, ov[4]); ov[5] = fmaf(o1[q].y, wgt, ov[5]); ov[6] = fmaf(o1[q].z, wgt, ov[6]); ov[7] = fmaf(o1[q].w, wgt, ov[7]);
+                        }
                     }
                     const float inv = 1.0f / Lt;
                     uint4 r; half2* hh = reinterpret_cast<half2*>(&r);
@@ -669,33 +733,29 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                 });
             }
             consumer_sync();
+            stamp(l, 6);
             gemv(p, u0, u1);
             jbase += u1 - u0;
+            preload_norm(L->ln2, phase_of(a, PH_GU));
+            stamp(l, 7);
         }
-        grid_barrier(a.bar, (unsigned)G, gen, tid);
+        grid_barrier(a.bar, target, (unsigned)G, tid);
+        stamp(l, 8);
 
         // ========================================================= GU ========================================================
         {
             const Phase p = phase_of(a, PH_GU);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
-            residual_and_norm(a.acc_o);
-            if (u1 > u0) {
-                const half* nw = L->ln2;
-                const half2 rm2 = __float2half2_rn(s_rm);
-                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
-                    uint4 xv = reinterpret_cast<const uint4*>(xres)[k8];
-                    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(nw) + k8);
-                    half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
-                    #pragma unroll
-                    for (int i = 0; i < 4; i++) h[i] = __hmul2(__hmul2(h[i], rm2), w2[i]);
-                    return xv;
-                });
-            }
+            rm = residual_and_norm(a.acc_o);
+            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(L->ln2, rm));
             consumer_sync();
+            stamp(l, 9);
             gemv(p, u0, u1);
             jbase += u1 - u0;
+            stamp(l, 10);
         }
-        grid_barrier(a.bar, (unsigned)G, gen, tid);
+        grid_barrier(a.bar, target, (unsigned)G, tid);
+        stamp(l, 11);
 
         // ======================================================== DOWN =======================================================
         {
@@ -703,7 +763,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
             zero_share(a.acc_o, a.H);
             if (u1 > u0) {
-                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8) -> uint4 {
+                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
                     // silu(gate) * up on the fp16-rounded projections (q4_mlp.cu:27-36,46-88)
                     const float4 g0 = ldcg4(a.acc_gu + k8 * 8), g1 = ldcg4(a.acc_gu + k8 * 8 + 4);
                     const float4 u0v = ldcg4(a.acc_gu + a.I + k8 * 8), u1v = ldcg4(a.acc_gu + a.I + k8 * 8 + 4);
@@ -716,21 +776,25 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                 });
             }
             consumer_sync();
+            stamp(l, 12);
             gemv(p, u0, u1);
             jbase += u1 - u0;
+            if (l + 1 < a.n_layers) preload_norm(a.layers[l + 1].ln1, phase_of(a, PH_QKV));
+            stamp(l, 13);
         }
-        grid_barrier(a.bar, (unsigned)G, gen, tid);
+        grid_barrier(a.bar, target, (unsigned)G, tid);
+        stamp(l, 14);
     }
 
     // ========================================================= HEAD ==========================================================
-    residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr);
+    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr);
     if (a.x_out && cta == 0)
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
     if (a.lm_head) {
         const Phase p = phase_of(a, PH_HEAD);
         const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
         {
-            const half2 rm2 = __float2half2_rn(s_rm);
+            const half2 rm2 = __float2half2_rn(rm);
             for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
                 uint4 xv = reinterpret_cast<const uint4*>(xres)[i];
                 const uint4 wv = __ldg(reinterpret_cast<const uint4*>(a.final_norm) + i);
@@ -741,46 +805,40 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
         }
         consumer_sync();
-        // stage = 8 chunks of 512 fp16 of the row-major [vocab, H] matrix; stage j of the CTA goes to warp j & 15
+        // stage = 8 chunks of 512 fp16 of the row-major [vocab, H] matrix; the 4 warps of the pipeline take 2 chunks each
         const int cpr = a.H >> 9;                               // chunks per vocabulary row
         const long long nchunks = (long long)a.vocab * cpr;
-        int i = (int)((warp - jbase) & 15);
-        if (i < u1 - u0) {
-            long long j = jbase + i;
-            int slot = (int)(j % nst); uint32_t par = (uint32_t)((j / nst) & 1);
-            const uint32_t xh_a = smem_u32(xh);
-            for (; i < u1 - u0; i += 16) {
-                mbar_wait(full0 + slot * 8, par);
-                const uint32_t sb = ring_a + (uint32_t)slot * STAGE_STRIDE;
-                const long long c0 = (long long)(u0 + i) * 8;
-                long long row = c0 / cpr; int kc = (int)(c0 - row * cpr);
-                float part = 0.f;
-                #pragma unroll 1
-                for (int cc = 0; cc < 8 && c0 + cc < nchunks; cc++) {
+        for (int u = u0 + (int)((wk - jbase) & 3); u < u1; u += 4) {
+            mbar_wait(full0 + ls * 8, par);
+            const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
+            const long long c0 = (long long)u * 8 + wn * 2;
+            long long row = c0 / cpr; int kc = (int)(c0 - row * cpr);
+            float part = 0.f;
+            #pragma unroll 1
+            for (int cc = 0; cc < ((a.debug & 4) ? 0 : 2) && c0 + cc < nchunks; cc++) {
+                #pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(sb + (wn * 2 + cc) * 1024 + hf * 512 + lane * 16);
+                    const uint4 xv = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(xh) + (size_t)kc * 1024 + hf * 512 + lane * 16);
+                    const half2* wh = reinterpret_cast<const half2*>(&wv); const half2* xq = reinterpret_cast<const half2*>(&xv);
                     #pragma unroll
-                    for (int hf = 0; hf < 2; hf++) {
-                        const uint4 wv = lds128(sb + cc * 1024 + hf * 512 + lane * 16);
-                        const uint4 xv = lds128(xh_a + (uint32_t)kc * 1024u + hf * 512 + lane * 16);
-                        const half2* wh = reinterpret_cast<const half2*>(&wv); const half2* xq = reinterpret_cast<const half2*>(&xv);
-                        #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const float2 fw = __half22float2(wh[q]), fx = __half22float2(xq[q]);
-                            part = fmaf(fw.x, fx.x, part); part = fmaf(fw.y, fx.y, part);
-                        }
-                    }
-                    if (++kc == cpr || cc == 7 || c0 + cc + 1 == nchunks) {
-                        float tot = part;
-                        #pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
-                        if (lane == 0) atomicAdd(a.logits + row, tot);
-                        part = 0.f;
-                        if (kc == cpr) { kc = 0; row++; }
+                    for (int q = 0; q < 4; q++) {
+                        const float2 fw = __half22float2(wh[q]), fx = __half22float2(xq[q]);
+                        part = fmaf(fw.x, fx.x, part); part = fmaf(fw.y, fx.y, part);
                     }
                 }
-                __syncwarp();
-                if (lane < 4) mbar_arrive(empty0 + slot * 8);
-                slot += 16; while (slot >= nst) { slot -= nst; par ^= 1u; }
+                if (++kc == cpr || cc == 1 || c0 + cc + 1 == nchunks) {
+                    float tot = part;
+                    #pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                    if (lane == 0) atomicAdd(a.logits + row, tot);
+                    part = 0.f;
+                    if (kc == cpr) { kc = 0; row++; }
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + ls * 8);
+            if (++ls == depth) { ls = 0; par ^= 1u; }
         }
     }
 }
@@ -832,7 +890,8 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
                 return exl_set_err(EXL_ERR_ARG, "decode_plan: layer %d matrix %d is %d x %d, expected %d x %d", l, i, w->K, w->N, expectK[i], expectN[i]);
             const bool one = q0->groups == 1;
             if ((one && w->groups != 1) || (!one && w->groupsize != gs)) return exl_set_err(EXL_ERR_ARG, "decode_plan: mixed group sizes");
-            L[l].tm[i] = w->tmap_w; L[l].qz[i] = w->qzeros; L[l].sc[i] = w->scales;
+            if (!w->valid3) return exl_set_err(EXL_ERR_ARG, "decode_plan: layer %d matrix %d has no unit tensor maps (width %% 128 != 0)", l, i);
+            L[l].tw[i] = w->tmap_w3; L[l].ts[i] = w->tmap_sc; L[l].tz[i] = w->tmap_qz;
         }
         L[l].ln1 = (const half*)d->ln1[l]; L[l].ln2 = (const half*)d->ln2[l];
         L[l].kc = (half*)d->key_cache[l]; L[l].vc = (half*)d->value_cache[l];
@@ -848,12 +907,14 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     a.spt_max = (H > I ? H : I) / TILE; if (HQ / TILE > a.spt_max) a.spt_max = HQ / TILE;
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
-    const size_t fixed = 1024 + (size_t)a.spt_max * (256 + 32) + (size_t)H * 2 + (size_t)(17 * PART_LD + 3 * TILE) * 4 + 1024 /* static */;
-    int nst = (int)(((size_t)dev_smem - fixed) / STAGE_STRIDE);
-    if (const char* e = getenv("EXL_DS_NST")) { int v = atoi(e); if (v >= 4 && v < nst) nst = v; }
-    if (nst > 20) nst = 20;
-    if (nst < 6) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: model too wide for the shared-memory plan (ring of %d stages)", nst));
-    a.nst = nst;
+    const size_t fixed = 1024 + (size_t)a.spt_max * (256 + 32) + (size_t)H * 2 + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + 1024 /* static */;
+    int depth = (int)(((size_t)dev_smem - fixed) / STAGE_STRIDE) / 4;
+    if (const char* e = getenv("EXL_DS_DEPTH")) { int v = atoi(e); if (v >= 1 && v < depth) depth = v; }
+    if (depth > MAX_DEPTH) depth = MAX_DEPTH;
+    if (depth < 2) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: model too wide for the shared-memory plan (%d ring stages per pipeline)", depth));
+    if (d->num_heads > ds->num_sms) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: more heads (%d) than SMs", d->num_heads));
+    a.depth = depth;
+    const int nst = 4 * depth;
     p->smem = fixed - 1024 + (size_t)nst * STAGE_STRIDE;
     if ((size_t)H * 2 > (size_t)a.spt_max * 256) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: internal: head staging does not fit"));
     cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
@@ -869,6 +930,8 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_qkv = take((size_t)3 * HQ * 4), o_o = take((size_t)H * 4), o_gu = take((size_t)2 * I * 4), o_d = take((size_t)H * 4);
     const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256);
+    const bool want_trace = getenv("EXL_DS_TRACE") != nullptr;
+    const size_t o_trace = want_trace ? take((size_t)p->grid * TRACE_LAYERS * 16 * 8) : 0;
     if (cudaMalloc(&p->d_scratch, off) != cudaSuccess || cudaMalloc(&p->d_layers, sizeof(LayerDesc) * L.size()) != cudaSuccess)
         return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: cudaMalloc failed"));
     if (cudaMemset(p->d_scratch, 0, off) != cudaSuccess ||
@@ -876,7 +939,9 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
         return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: upload failed"));
     a.layers = p->d_layers;
     a.acc_qkv = (float*)(p->d_scratch + o_qkv); a.acc_o = (float*)(p->d_scratch + o_o); a.acc_gu = (float*)(p->d_scratch + o_gu);
-    a.acc_d = (float*)(p->d_scratch + o_d); a.att_part = (float*)(p->d_scratch + o_att); a.bar = (unsigned*)(p->d_scratch + o_bar);
+    a.acc_d = (float*)(p->d_scratch + o_d); a.att_part = (float*)(p->d_scratch + o_att); a.bar = (unsigned long long*)(p->d_scratch + o_bar);
+    if (const char* ed = getenv("EXL_DS_DEBUG")) a.debug = atoi(ed);
+    a.trace = want_trace ? (unsigned long long*)(p->d_scratch + o_trace) : nullptr;
     *out = p;
     return EXL_OK;
 }
@@ -893,8 +958,19 @@ extern "C" int exl_decode_plan_destroy(exl_decode_plan* p)
 extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step)
 {
     if (!p) return exl_set_err(EXL_ERR_STATE, "decode_plan_info: NULL plan");
-    if (grid) *grid = p->grid; if (ring_stages) *ring_stages = p->args.nst; if (smem_bytes) *smem_bytes = (int64_t)p->smem;
+    if (grid) *grid = p->grid; if (ring_stages) *ring_stages = 4 * p->args.depth; if (smem_bytes) *smem_bytes = (int64_t)p->smem;
     if (barriers_per_step) *barriers_per_step = 1 + 5 * (int64_t)p->args.n_layers;
+    return EXL_OK;
+}
+
+// EXL_DS_TRACE=1 at plan creation: copies the [grid][4 layers][16 events] globaltimer stamps of the last launch to the host
+extern "C" int exl_decode_plan_trace(exl_decode_plan* p, unsigned long long* out_host, int64_t capacity)
+{
+    if (!p || !p->args.trace) return exl_set_err(EXL_ERR_STATE, "decode_plan_trace: plan has no trace buffer (set EXL_DS_TRACE=1 before creating it)");
+    const int64_t n = (int64_t)p->grid * TRACE_LAYERS * 16;
+    if (capacity < n) return exl_set_err(EXL_ERR_ARG, "decode_plan_trace: need room for %lld values", (long long)n);
+    DeviceGuard guard(p->device);
+    EXL_CUDA_TRY(cudaMemcpy(out_host, p->args.trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return EXL_OK;
 }
 

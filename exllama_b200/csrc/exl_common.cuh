@@ -28,6 +28,15 @@ struct exl_q4_matrix
     alignas(64) CUtensorMap tmap_w;
     // same tensor, box 8 rows x 128 columns, no swizzle: the packed-word tile of one k-block of the tcgen05 GEMM (q4_gemm_tc.cu)
     alignas(64) CUtensorMap tmap_wp;
+    // decode_step.cu: ONE op per 8 KB unit -- qweight viewed as [N/32][K/8][32] (dims fastest first: 32 columns, k8-row, column group),
+    // box 32 x 16 x 4 with the 128-byte swizzle: the same shared-memory image as four tmap_w boxes side by side.  valid3 == 0 when
+    // N % 32 != 0.
+    alignas(64) CUtensorMap tmap_w3;
+    // scales [groups, N] fp16, box 128 columns x R group rows; qzeros [groups, N/8] u32, box 16 words x R rows;
+    // R = group rows per 128-row K stage (groupsize 32: 4, 64: 2, >= 128: 1)
+    alignas(64) CUtensorMap tmap_sc;
+    alignas(64) CUtensorMap tmap_qz;
+    int valid3;
 };
 
 struct ExlTuning

@@ -83,6 +83,33 @@ int exl_encode_weight_tmap(exl_q4_matrix* w)
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled (prefill box) failed (%d) for K=%d N=%d", (int)r, w->K, w->N);
+    w->valid3 = 0;
+    if (w->N % 128 == 0 && w->K % 128 == 0) {
+        const cuuint64_t d3[3] = {32, (cuuint64_t)(w->K / 8), (cuuint64_t)(w->N / 32)};
+        const cuuint64_t s3[2] = {(cuuint64_t)w->N * 4, 128};           // bytes: next k8-row, next column group
+        const cuuint32_t b3[3] = {32, 16, 4};
+        const cuuint32_t e3[3] = {1, 1, 1};
+        r = encode(&w->tmap_w3, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)w->qweight, d3, s3, b3, e3,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled (3-D unit box) failed (%d) for K=%d N=%d", (int)r, w->K, w->N);
+        const cuuint32_t R = (w->groups > 1 && w->groupsize < 128 && 128 % w->groupsize == 0) ? (cuuint32_t)(128 / w->groupsize) : 1u;
+        const cuuint64_t dsc[2] = {(cuuint64_t)w->N, (cuuint64_t)w->groups};
+        const cuuint64_t ssc[1] = {(cuuint64_t)w->N * 2};
+        const cuuint32_t bsc[2] = {128, R};
+        r = encode(&w->tmap_sc, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w->scales, dsc, ssc, bsc, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled (scales) failed (%d)", (int)r);
+        const cuuint64_t dqz[2] = {(cuuint64_t)(w->N / 8), (cuuint64_t)w->groups};
+        const cuuint64_t sqz[1] = {(cuuint64_t)(w->N / 8) * 4};
+        const cuuint32_t bqz[2] = {16, R};
+        r = encode(&w->tmap_qz, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)w->qzeros, dqz, sqz, bqz, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return exl_set_err(EXL_ERR_CUDA, "cuTensorMapEncodeTiled (qzeros) failed (%d)", (int)r);
+        w->valid3 = 1;
+    }
     return EXL_OK;
 }
 

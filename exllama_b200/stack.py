@@ -14,8 +14,6 @@ of each row-parallel projection is summed with ONE all-reduce (exllama_b200/tp.p
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
-
 import torch
 
 from . import cuda_ext
@@ -24,28 +22,7 @@ from . import tp as tpmod
 ext = cuda_ext.exllama_ext
 
 
-@dataclass
-class LlamaShape:
-    name: str
-    hidden: int
-    inter: int
-    layers: int
-    heads: int
-    head_dim: int = 128
-    vocab: int = 32000
-    eps: float = 1e-6
-
-    @property
-    def kv_heads(self):
-        return self.heads
-
-
-SHAPES = {
-    "7b": LlamaShape("llama-7b", 4096, 11008, 32, 32),
-    "13b": LlamaShape("llama-13b", 5120, 13824, 40, 40),
-    "33b": LlamaShape("llama-33b", 6656, 17920, 60, 52),
-    "65b": LlamaShape("llama-65b", 8192, 22016, 80, 64),
-}
+from .shapes import SHAPES, LlamaShape  # noqa: E402,F401  (re-exported)
 
 
 def synth_q4_device(K, N, groupsize, device, gen, act_order=False, scale_lo=2e-4, scale_hi=2e-3):

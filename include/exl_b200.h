@@ -181,6 +181,10 @@ int exl_decode_plan_create(const exl_decode_desc* desc, exl_decode_plan** out_pl
 int exl_decode_plan_destroy(exl_decode_plan* plan);
 int exl_decode_plan_info(const exl_decode_plan* plan, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step);
 
+/* Bring-up aid: with EXL_DS_TRACE=1 in the environment when the plan is created, every CTA stamps %globaltimer at its phase
+   boundaries of the first 4 layers; this copies the [grid][4][16] stamps of the last launch to the host. */
+int exl_decode_plan_trace(exl_decode_plan* plan, unsigned long long* out_host, int64_t capacity);
+
 /* One token: x_in half [hidden] (the embedding row), attends over cache rows [0, past_len) plus the new row, which it
    writes at past_len.  x_out (optional) receives the final hidden state before the final norm, logits float [vocab]
    (required iff the plan has an lm_head).  CUDA-graph capturable; successive calls need no host synchronisation. */

@@ -330,6 +330,16 @@ void orc_q4_matmul_cpu_f32(const half_t* x, int M, int K, int N,
     free(xf);
 }
 
+/* explicit thread count (torchrun exports OMP_NUM_THREADS=1 to its children; the CPU baseline must not inherit that) */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -176,6 +176,10 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(_i(int(n)))
+
+
 def half_matmul_f64(x, w, acc_in=None) -> np.ndarray:
     M, K = x.shape
     N = w.shape[1]
