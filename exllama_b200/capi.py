@@ -263,9 +263,10 @@ class DecodePlan:
         """[grid, 4 layers, 16 events] globaltimer stamps (ns) of the last launch (EXL_DS_TRACE=1 at creation)."""
         import numpy as np
         g = self.info()["grid"]
-        out = np.zeros((g, 4, 16), dtype=np.uint64)
+        out = np.zeros(g * (4 * 16 + 96), dtype=np.uint64)
         check(lib().exl_decode_plan_trace(self.handle, out.ctypes.data_as(vp), out.size))
-        return out
+        self.fine_trace = out[g * 64:].reshape(g, 32, 3)       # layer 2, GU phase, warp 0: per stage {wait start, data ready, done}
+        return out[:g * 64].reshape(g, 4, 16)
 
     def close(self):
         if self.handle:

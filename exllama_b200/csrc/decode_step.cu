@@ -443,7 +443,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
 
     // ---- GEMV phase body: this pipeline's stages of the CTA's unit range, this warp's 32 columns ----
-    auto gemv = [&](const Phase& p, int u0, int u1) {
+    auto gemv = [&](const Phase& p, int u0, int u1, bool fine = false) {
+        unsigned long long* ft = (fine && a.trace && warp == 0 && lane == 0) ? a.trace + (size_t)G * TRACE_LAYERS * 16 + (size_t)cta * 96 : nullptr;
+        int fk = 0;
         int u = u0 + (int)((wk - jbase) & 3);                // stage j of the CTA goes to pipeline j & 3
         if (u >= u1) return;
         int tile = u / p.spt, s = u - tile * p.spt;
@@ -460,7 +462,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         };
         for (; u < u1; u += 4) {
             if (tile != cur_tile) { flush_tile(); cur_tile = tile; }
+            if (ft && fk < 32) ft[fk * 3] = gtime();
             mbar_wait(full0 + ls * 8, par);
+            if (ft && fk < 32) ft[fk * 3 + 1] = gtime();
             if (!(a.debug & 1)) {
                 const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
                 const unsigned char* xrow = xs + (size_t)s * 256 + t * 16 + (g & 1) * 8;
@@ -510,6 +514,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + ls * 8);
+            if (ft && fk < 32) { ft[fk * 3 + 2] = gtime(); fk++; }
             if (++ls == depth) { ls = 0; par ^= 1u; }
             s += 4; while (s >= p.spt) { s -= p.spt; tile++; }
         }
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(L->ln2, rm));
             consumer_sync();
             stamp(l, 9);
-            gemv(p, u0, u1);
+            gemv(p, u0, u1, l == 2);
             jbase += u1 - u0;
             stamp(l, 10);
         }
@@ -931,7 +936,7 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     const size_t o_qkv = take((size_t)3 * HQ * 4), o_o = take((size_t)H * 4), o_gu = take((size_t)2 * I * 4), o_d = take((size_t)H * 4);
     const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256);
     const bool want_trace = getenv("EXL_DS_TRACE") != nullptr;
-    const size_t o_trace = want_trace ? take((size_t)p->grid * TRACE_LAYERS * 16 * 8) : 0;
+    const size_t o_trace = want_trace ? take((size_t)p->grid * (TRACE_LAYERS * 16 + 96) * 8) : 0;
     if (cudaMalloc(&p->d_scratch, off) != cudaSuccess || cudaMalloc(&p->d_layers, sizeof(LayerDesc) * L.size()) != cudaSuccess)
         return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: cudaMalloc failed"));
     if (cudaMemset(p->d_scratch, 0, off) != cudaSuccess ||
@@ -967,7 +972,7 @@ extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ri
 extern "C" int exl_decode_plan_trace(exl_decode_plan* p, unsigned long long* out_host, int64_t capacity)
 {
     if (!p || !p->args.trace) return exl_set_err(EXL_ERR_STATE, "decode_plan_trace: plan has no trace buffer (set EXL_DS_TRACE=1 before creating it)");
-    const int64_t n = (int64_t)p->grid * TRACE_LAYERS * 16;
+    const int64_t n = (int64_t)p->grid * (TRACE_LAYERS * 16 + 96);
     if (capacity < n) return exl_set_err(EXL_ERR_ARG, "decode_plan_trace: need room for %lld values", (long long)n);
     DeviceGuard guard(p->device);
     EXL_CUDA_TRY(cudaMemcpy(out_host, p->args.trace, (size_t)n * 8, cudaMemcpyDeviceToHost));

@@ -41,3 +41,11 @@ print(json.dumps({"debug": os.environ.get("EXL_DS_DEBUG"), "nst": os.environ.get
                   "ms_per_step": round(ms, 4), "layer_us": round(layer_us, 2), "plan": st.dplan.info()}))
 for r in rows:
     print(json.dumps(r))
+
+ft = st.dplan.fine_trace.astype(np.int64)
+for c in (0, 73, 147):
+    f = ft[c]; n = int((f[:, 2] > 0).sum())
+    if n == 0: continue
+    t0 = f[0, 0]
+    print(json.dumps({"cta": c, "stages": n, "wait_us": [round((f[k, 1] - f[k, 0]) / 1e3, 2) for k in range(n)],
+                      "work_us": [round((f[k, 2] - f[k, 1]) / 1e3, 2) for k in range(n)], "end_us": round((f[n - 1, 2] - t0) / 1e3, 2)}))
