@@ -244,7 +244,7 @@ def main():
         from exllama_b200 import tp as tpmod
         tpmod.init_fused_allreduce(ext, dev.index)      # row-parallel projections: GEMV + peer-memory all-reduce in one kernel
         fused_ar = True
-    use_step = world == 1 and not args.act_order and not args.no_fused_step
+    use_step = not args.act_order and not args.no_fused_step
     if use_step:
         stack.make_plan()
     torch.cuda.synchronize()
@@ -304,7 +304,7 @@ def main():
     if use_step:
         step_device = fused_step                   # ONE launch per token: no graph needed
         launches_per_step = 1
-        mode = "one persistent kernel per token (exl_decode_step)"
+        mode = "one persistent kernel per token (exl_decode_step)" + (f", {world} ranks: partials reduced over NVLink peer memory inside the kernel" if world > 1 else "")
         graph = None
     else:
         # NCCL inside stream capture hung on this stack; the fused all-reduce kernels are plain launches and capture fine
@@ -527,7 +527,8 @@ def main():
             "config": {"workload": workload_name(shape, gs, args.act_order, args.ctx, args.seq)},      # identical in both arms
             "run": {"detail": f"{shape.layers} layers x (norm, q/k/v, rope, cache write, attention over {past} cached positions, o_proj, norm, gate/up, silu*mul, down) + final norm + fp16 lm_head",
                        "decode_mode": mode, "parallelism": f"tp{world}", "cuda_graph": graph is not None,
-                       "allreduce": ("fused GEMV epilogue over NVLink peer memory" if fused_ar else ("nccl" if world > 1 else None)),
+                       "allreduce": (("inside decode_step_kernel: peer-memory reductions + cross-GPU barrier" if use_step else
+                                      ("fused GEMV epilogue over NVLink peer memory" if fused_ar else "nccl")) if world > 1 else None),
                        "l2": f"weights ({(wbytes + head_bytes) / 1e9:.2f} GB/token/rank) >> L2 (126 MB): every step streams them from HBM"},
             "e2e": {"value": round(1000.0 / e2e_ms, 2), "unit": "tok/s", "h2d_bytes_per_step": host_in.numel() * 2,
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(e2e_ms, 4),

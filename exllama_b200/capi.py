@@ -56,6 +56,8 @@ SIGNATURES = {
     "exl_decode_plan_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
     "exl_decode_step": (i32, [vp, vp, i32, vp, vp, vp]),
     "exl_decode_plan_trace": (i32, [vp, vp, i64]),
+    "exl_decode_plan_ipc_export": (i32, [vp, vp]),
+    "exl_decode_plan_ipc_import": (i32, [vp, vp, i32]),
     "exl_launch_count": (i64, []),
     "exl_last_q4_path": (C.c_char_p, []),
 }
@@ -218,7 +220,8 @@ class _DecodeDesc(C.Structure):
     """struct exl_decode_desc (include/exl_b200.h)"""
     _fields_ = [("n_layers", i32), ("num_heads", i32), ("head_dim", i32), ("max_seq_len", i32), ("vocab", i32), ("rms_eps", f32),
                 ("mats", C.POINTER(vp)), ("ln1", C.POINTER(vp)), ("ln2", C.POINTER(vp)), ("key_cache", C.POINTER(vp)),
-                ("value_cache", C.POINTER(vp)), ("sin", vp), ("cos", vp), ("final_norm", vp), ("lm_head", vp)]
+                ("value_cache", C.POINTER(vp)), ("sin", vp), ("cos", vp), ("final_norm", vp), ("lm_head", vp),
+                ("tp_rank", i32), ("tp_world", i32)]
 
 
 class DecodePlan:
@@ -228,7 +231,7 @@ class DecodePlan:
     borrowed and must outlive the plan."""
 
     def __init__(self, handles, ln1, ln2, key_cache, value_cache, sin, cos, num_heads, head_dim, max_seq_len, eps,
-                 final_norm=None, lm_head=None):
+                 final_norm=None, lm_head=None, tp_rank=0, tp_world=1):
         n = len(handles)
         self._keep = (ln1, ln2, key_cache, value_cache, sin, cos, final_norm, lm_head)
         flat = []
@@ -247,9 +250,23 @@ class DecodePlan:
         d.sin, d.cos = sin.data_ptr(), cos.data_ptr()
         d.final_norm = final_norm.data_ptr() if final_norm is not None else None
         d.lm_head = lm_head.data_ptr() if lm_head is not None else None
+        d.tp_rank, d.tp_world = tp_rank, tp_world
         self.vocab = d.vocab
+        self.tp_world = tp_world
         self.handle = vp()
         check(lib().exl_decode_plan_create(C.byref(d), C.byref(self.handle)))
+
+    def ipc_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        check(lib().exl_decode_plan_ipc_export(self.handle, C.cast(buf, vp)))
+        return bytes(buf)
+
+    def ipc_import(self, handles):
+        """handles: list of `world` 64-byte handles in rank order (as gathered from every rank's ipc_export())."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.tp_world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(lib().exl_decode_plan_ipc_import(self.handle, C.cast(buf, vp), self.tp_world))
 
     def info(self):
         g, r, s, b = i32(), i32(), i64(), i64()
@@ -263,10 +280,9 @@ class DecodePlan:
         """[grid, 4 layers, 16 events] globaltimer stamps (ns) of the last launch (EXL_DS_TRACE=1 at creation)."""
         import numpy as np
         g = self.info()["grid"]
-        out = np.zeros(g * (4 * 16 + 96), dtype=np.uint64)
+        out = np.zeros((g, 4, 16), dtype=np.uint64)
         check(lib().exl_decode_plan_trace(self.handle, out.ctypes.data_as(vp), out.size))
-        self.fine_trace = out[g * 64:].reshape(g, 32, 3)       # layer 2, GU phase, warp 0: per stage {wait start, data ready, done}
-        return out[:g * 64].reshape(g, 4, 16)
+        return out
 
     def close(self):
         if self.handle:

@@ -35,6 +35,7 @@
 // (or one group), no act-order, widths multiples of 128.  Every wait is bounded by wall time and traps on expiry.
 #include "exl_common.cuh"
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -80,7 +81,14 @@ struct StepArgs
     const half* final_norm; const half* lm_head; float* logits; int vocab;     // optional head
     float* acc_qkv; float* acc_o; float* acc_gu; float* acc_d;                 // fp32 phase accumulators in L2
     float* att_part; int att_slots;    // [heads][att_slots][PART_LD]
-    unsigned long long* bar;           // grid barrier: monotonic arrival counter
+    unsigned long long* bar;           // grid barrier: monotonic arrival counter (this GPU's CTAs only)
+    // tensor parallel (world > 1): the row-parallel projections (o_proj, down_proj) add their partials into EVERY rank's accumulator
+    // over NVLink peer memory, and the barrier that follows them is a cross-GPU barrier (every CTA of every rank arrives on every
+    // rank's cross counter) -- the all-reduce is the split-K reduction, there is no separate collective.
+    int tp_rank, tp_world;
+    float* peer_o[8]; float* peer_d[8];          // acc_o / acc_d of every rank, mapped here (own entry == acc_o / acc_d)
+    unsigned long long* peer_bar[8];             // cross-barrier counter of every rank
+    unsigned long long* bar_x;                   // own cross-barrier counter (== peer_bar[tp_rank])
     int debug;                         // EXL_DS_DEBUG bitmask (bring-up experiments): 1 skip GEMV math, 2 skip attention math, 4 skip head math
     unsigned long long* trace;         // optional [G][TRACE_LAYERS][16] globaltimer stamps of CTA thread 0 (EXL_DS_TRACE=1), else NULL
 };
@@ -125,6 +133,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tma
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
+// wait that hands back a zero "token": adding it to the addresses of the loads that follow makes them data-dependent on the wait, so
+// the (non-volatile, freely schedulable) shared-memory loads below can never be hoisted above it
+__device__ __forceinline__ uint32_t mbar_wait_tok(uint32_t bar, uint32_t parity, bool already)
+{
+    if (!already) mbar_wait(bar, parity);
+    uint32_t z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z) :: "memory");
+    return z;
+}
+// arrive that consumes a value computed from the stage's data: it cannot be scheduled before the loads it releases
+__device__ __forceinline__ void mbar_arrive_dep(uint32_t bar, float dep)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar), "f"(dep) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 r; asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 r; asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t r; asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d)
 {
@@ -186,15 +217,15 @@ __device__ __forceinline__ int share_lo(long long n, int c, int G) { return (int
 // the CTA whose share contains item u (inverse of share_lo)
 __device__ __forceinline__ int cta_of(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
 
-struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; };     // tpm: tiles per matrix (ATT: units per head)
+struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; float* const* peers; };     // tpm: tiles per matrix (ATT: units per head)
 
 __device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
 {
-    Phase p; p.kind = kind; p.acc = nullptr; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
+    Phase p; p.kind = kind; p.acc = nullptr; p.peers = nullptr; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
     if (kind == PH_QKV)       { p.spt = a.H / TILE;  p.N = a.HQ; p.nmat = 3; p.mat0 = 0; p.acc = a.acc_qkv; }
-    else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; }
+    else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; p.peers = a.tp_world > 1 ? a.peer_o : nullptr; }
     else if (kind == PH_GU)   { p.spt = a.H / TILE;  p.N = a.I;  p.nmat = 2; p.mat0 = 4; p.acc = a.acc_gu; }
-    else if (kind == PH_DOWN) { p.spt = a.I / TILE;  p.N = a.H;  p.nmat = 1; p.mat0 = 6; p.acc = a.acc_d; }
+    else if (kind == PH_DOWN) { p.spt = a.I / TILE;  p.N = a.H;  p.nmat = 1; p.mat0 = 6; p.acc = a.acc_d; p.peers = a.tp_world > 1 ? a.peer_d : nullptr; }
     if (kind == PH_ATT) {
         const int nch = (a.past_len + 15) >> 4;
         p.tpm = nch > 0 ? nch : 1;                          // units per head (one empty unit when there is no history)
@@ -231,6 +262,27 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
     consumer_sync();
 }
 
+// Cross-GPU barrier (tensor parallel): every CTA of every rank adds 1 to the cross counter of EVERY rank with release semantics at
+// system scope -- which also orders this CTA's earlier peer-memory reductions before the arrival -- and polls its own counter.
+__device__ __forceinline__ void cross_barrier(unsigned long long* const* peer_bar, int world, unsigned long long* own, unsigned long long& target,
+                                              unsigned nctas, int tid)
+{
+    consumer_sync();
+    if (tid == 0) {
+        for (int r = 0; r < world; r++)
+            asm volatile("red.release.sys.global.add.u64 [%0], 1;" :: "l"(peer_bar[r]) : "memory");
+        unsigned long long v;
+        const unsigned long long t0 = gtime();
+        unsigned i = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(own) : "memory");
+            if ((++i & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
+        } while (v < target);
+    }
+    target += (unsigned long long)nctas * world;
+    consumer_sync();
+}
+
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -243,10 +295,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     float* q_s = parts + 2 * 17 * PART_LD;                                             // [2][128] scaled q of the segment's head
     float* kn_s = q_s + 2 * TILE;                                                      // [2][128] newest k row (after rope)
     float* vn_s = kn_s + 2 * TILE;                                                     // [2][128] newest v row
+    unsigned char* wnorm = reinterpret_cast<unsigned char*>(vn_s + 2 * TILE);          // [H / 8][16 B]: norm weights of the rows this CTA quantises next (by k8-row slot)
     half* xh = reinterpret_cast<half*>(xs);                                            // HEAD: normalised x [H] (xs is free by then)
     __shared__ __align__(8) unsigned long long full_bar[4 * MAX_DEPTH], empty_bar[4 * MAX_DEPTH];
     __shared__ float s_red[DS_NCW];
-    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_base, s_base_x;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -263,7 +316,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         int ls = 0; uint32_t par = 0; int issued = 0;                       // ls: stage inside the pipeline's ring; par: parity of the empty completion to wait for
         const uint32_t ring_a = smem_u32(ring) + (uint32_t)pq * depth * STAGE_STRIDE;
         const uint32_t full0 = smem_u32(&full_bar[pq * depth]), empty0 = smem_u32(&empty_bar[pq * depth]);
-        long long jbase = 0;
+        int jbase = 0;
         auto acquire = [&](uint32_t tx) -> uint32_t {
             if (issued >= depth) mbar_wait(empty0 + ls * 8, par ^ 1u);
             if (lane == 0) mbar_expect_tx(full0 + ls * 8, tx);
@@ -279,7 +332,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             for (int ph = PH_QKV; ph <= PH_DOWN; ph++) {
                 const Phase p = phase_of(a, ph);
                 const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
-                const int i0 = (int)((pq - jbase) & 3);
+                const int i0 = ((pq - jbase) & 3);
                 jbase += u1 - u0;
                 if (ph == PH_ATT) {
                     #pragma unroll 1
@@ -318,7 +371,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_HEAD);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
-            const int i0 = (int)((pq - jbase) & 3);
+            const int i0 = ((pq - jbase) & 3);
             const long long total = (long long)a.vocab * a.H * 2;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.lm_head);
             #pragma unroll 1
@@ -342,14 +395,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     const uint32_t full0 = smem_u32(&full_bar[wk * depth]), empty0 = smem_u32(&empty_bar[wk * depth]);
     int ls = 0; uint32_t par = 0;                        // this pipeline's ring position (every warp of the pipeline visits every stage)
     auto stamp = [&](int l, int ev) { if (a.trace && tid == 0 && l < TRACE_LAYERS) a.trace[((size_t)cta * TRACE_LAYERS + l) * 16 + ev] = gtime(); };
-    long long jbase = 0;                                 // stages this CTA has been through (same count as the producers)
+    int jbase = 0;                                       // stages this CTA has been through (same count as the producers)
     if (tid == 0) {
         unsigned long long v;
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
         s_base = v - v % (unsigned long long)G;          // at most G - 1 CTAs of THIS launch can have arrived already
+        if (a.tp_world > 1) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar_x) : "memory");
+            const unsigned long long gw = (unsigned long long)G * a.tp_world;
+            s_base_x = v - v % gw;                       // a faster rank can be at most one cross barrier (< G * world arrivals) ahead
+        }
     }
     consumer_sync();
     unsigned long long target = s_base + (unsigned long long)G;
+    unsigned long long target_x = a.tp_world > 1 ? s_base_x + (unsigned long long)G * a.tp_world : 0ull;
 
     auto zero_share = [&](float* buf, int n) {            // this CTA's share of a float buffer (n % 4 == 0)
         const int lo = share_lo(n >> 2, cta, G), hi = share_lo(n >> 2, cta + 1, G);
@@ -357,31 +416,34 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
 
     // ---- launch start: all accumulators and the logits to zero (robust against an aborted previous launch), then barrier ----
-    zero_share(a.acc_qkv, 3 * a.HQ); zero_share(a.acc_o, a.H); zero_share(a.acc_gu, 2 * a.I); zero_share(a.acc_d, a.H);
+    // (tensor parallel: acc_o / acc_d also receive the peers' partials, possibly before this rank has even started -- they are kept
+    //  clean by the in-kernel schedule alone: acc_o is zeroed in every DOWN phase, acc_d in every ATT phase)
+    zero_share(a.acc_qkv, 3 * a.HQ); zero_share(a.acc_gu, 2 * a.I);
+    if (a.tp_world == 1) { zero_share(a.acc_o, a.H); zero_share(a.acc_d, a.H); }
     if (a.logits) zero_share(a.logits, a.vocab);
     for (int i = tid; i < a.H / 8; i += DS_CONSUMERS)
         reinterpret_cast<uint4*>(xres)[i] = __ldg(reinterpret_cast<const uint4*>(a.x_in) + i);
 
     const int rpg = a.gshift >= 2 ? 16 : (4 << a.gshift);          // k8-rows per quantisation segment (a segment never spans stages)
 
-    // Norm weights of the rows this thread will quantise in the NEXT norm phase: constants, so they are fetched BEFORE the grid
-    // barrier and the phase prologue is left with one L2 round trip (the accumulator) instead of two.
-    uint4 wpre[2];
+    // Norm weights of the rows this CTA will quantise in the NEXT norm phase are constants: they are copied into shared memory
+    // with cp.async BEFORE the grid barrier (no registers held), so the phase prologue is left with one L2 round trip (the
+    // accumulator) instead of two.  Slot r of wnorm holds the weights of row r of the staging order.
     auto preload_norm = [&](const half* nw, const Phase& p) {
         const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
         const int n = min(u1 - u0, p.spt), s0 = u1 > u0 ? u0 % p.spt : 0;
-        #pragma unroll
-        for (int it = 0; it < 2; it++) {
-            const int r = it * DS_CONSUMERS + tid;
+        for (int r = tid; r < n * 16; r += DS_CONSUMERS) {
             int s = s0 + (r >> 4); if (s >= p.spt) s -= p.spt;
-            wpre[it] = r < n * 16 ? __ldg(reinterpret_cast<const uint4*>(nw) + (s * 16 + (r & 15))) : make_uint4(0, 0, 0, 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(wnorm) + (uint32_t)r * 16u), "l"(nw + (size_t)(s * 16 + (r & 15)) * 8) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     preload_norm(a.layers[0].ln1, phase_of(a, PH_QKV));
     grid_barrier(a.bar, target, (unsigned)G, tid);
 
     // ---- residual add (fp16(x + fp32 delta), the rounding point of q4_matmul's no_zero epilogue) + row factor of the RMS norm ----
     auto residual_and_norm = [&](const float* delta) -> float {
+        asm volatile("cp.async.wait_all;" ::: "memory");
         float ss = 0.f;
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
             uint4 xv = reinterpret_cast<uint4*>(xres)[i];
@@ -430,10 +492,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
         }
     };
-    auto norm_get = [&](const half* nw, float rm) {
-        return [=, &wpre](int k8, int it) -> uint4 {
+    auto norm_get = [&](float rm) {
+        return [=](int k8, int it) -> uint4 {
             uint4 xv = reinterpret_cast<const uint4*>(xres)[k8];
-            const uint4 wv = it < 2 ? wpre[it] : __ldg(reinterpret_cast<const uint4*>(nw) + k8);
+            const uint4 wv = reinterpret_cast<const uint4*>(wnorm)[it * DS_CONSUMERS + tid];
             const half2 rm2 = __float2half2_rn(rm);
             half2* h = reinterpret_cast<half2*>(&xv); const half2* w2 = reinterpret_cast<const half2*>(&wv);
             #pragma unroll
@@ -443,82 +505,117 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
 
     // ---- GEMV phase body: this pipeline's stages of the CTA's unit range, this warp's 32 columns ----
-    auto gemv = [&](const Phase& p, int u0, int u1, bool fine = false) {
-        unsigned long long* ft = (fine && a.trace && warp == 0 && lane == 0) ? a.trace + (size_t)G * TRACE_LAYERS * 16 + (size_t)cta * 96 : nullptr;
-        int fk = 0;
-        int u = u0 + (int)((wk - jbase) & 3);                // stage j of the CTA goes to pipeline j & 3
+    // UPSEG = units (of 4 k8-rows = 32 k) per quantisation segment, compile-time: 4 (groupsize >= 128), 2 (64), 1 (32).
+    auto gemv_t = [&](auto upseg_c, const Phase& p, int u0, int u1) {
+        constexpr int UPSEG = decltype(upseg_c)::value;
+        int u = u0 + ((wk - jbase) & 3);                // stage j of the CTA goes to pipeline j & 3
         if (u >= u1) return;
         int tile = u / p.spt, s = u - tile * p.spt;
         int cur_tile = tile;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        int ia[8];
-        const int upseg = rpg >> 2;                          // units (of 4 k8-rows) per quantisation segment: 1, 2 or 4
         auto flush_tile = [&]() {
             if (t == 0) {
                 const int mi = cur_tile / p.tpm, col0 = (cur_tile - mi * p.tpm) * TILE;
-                red_add_v4(p.acc + (size_t)mi * p.N + col0 + lane_col, acc[0], acc[1], acc[2], acc[3]);
+                const size_t off = (size_t)mi * p.N + col0 + lane_col;
+                red_add_v4(p.acc + off, acc[0], acc[1], acc[2], acc[3]);
+                if (p.peers) {
+                    // row-parallel projection of a tensor-parallel layer: the same partial into every peer's accumulator (NVLink)
+                    for (int r = 0; r < a.tp_world; r++) {
+                        if (r == a.tp_rank) continue;
+                        float* d = p.peers[r] + off;
+                        #pragma unroll
+                        for (int c = 0; c < 4; c++) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(d + c), "f"(acc[c]) : "memory");
+                    }
+                }
             }
             acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         };
+        // every address below is a 32-bit shared-memory address built from per-lane constants computed once per phase
+        // B column n of the MMA is supplied by the lanes with g == n: 0 = high-byte plane of x, 1 = low-byte plane.  Columns 2..7 only
+        // feed D columns 2..7, which live in lanes t >= 1 and are never read -- so those lanes may load anything (they load plane g & 1).
+        const uint32_t x_lane = smem_u32(xs) + t * 16 + (g & 1) * 8;
+        constexpr uint32_t xstage = 256u, xunit = 64u;
+        const uint32_t w_lane = (uint32_t)(wn * BOX_BYTES + t * 128 + ((pg ^ t) << 4));              // k8-rows t, t + 8 (r & 7 == t)
+        const uint32_t w_lane4 = w_lane + 512u + ((pg & 4) ? -64 : 64);                              // k8-rows t + 4, t + 12: chunk (pg ^ t) ^ 4
+        const uint32_t sc_lane = (uint32_t)(META_SC + lane_col * 2), zq_lane = (uint32_t)(META_ZQ + (lane_col >> 3) * 4);
+        const uint32_t zshift = (uint32_t)((lane_col & 4) * 4);
+        const uint32_t seg_a = smem_u32(segt);
+        bool ready = mbar_try(full0 + ls * 8, par);
         for (; u < u1; u += 4) {
             if (tile != cur_tile) { flush_tile(); cur_tile = tile; }
-            if (ft && fk < 32) ft[fk * 3] = gtime();
-            mbar_wait(full0 + ls * 8, par);
-            if (ft && fk < 32) ft[fk * 3 + 1] = gtime();
+            const uint32_t tok = mbar_wait_tok(full0 + ls * 8, par, ready);
+            const int ls_cur = ls;
+            if (++ls == depth) { ls = 0; par ^= 1u; }
+            // probe the NEXT stage's barrier now: its ~90-cycle answer overlaps this stage's work
+            ready = (u + 4 < u1) ? mbar_try(full0 + ls * 8, par) : false;
+            float dep = 0.f;
             if (!(a.debug & 1)) {
-                const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
-                const unsigned char* xrow = xs + (size_t)s * 256 + t * 16 + (g & 1) * 8;
+                const uint32_t sb = ring_a + (uint32_t)ls_cur * STAGE_STRIDE + tok;
+                const uint32_t xr = x_lane + (uint32_t)s * xstage + tok;
                 uint4 w[4]; uint2 xv[4];
+                w[0] = lds128(sb + w_lane);         w[1] = lds128(sb + w_lane4);
+                w[2] = lds128(sb + w_lane + 1024);  w[3] = lds128(sb + w_lane4 + 1024);
                 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int r = q * 4 + t;                // k8-row of this lane inside the stage
-                    w[q] = *reinterpret_cast<const uint4*>(sb + wn * BOX_BYTES + r * 128 + ((pg ^ (r & 7)) << 4));
-                    xv[q] = *reinterpret_cast<const uint2*>(xrow + q * 64);
-                    if (g >= 2) xv[q] = make_uint2(0u, 0u);    // B column g: 0 = high-byte plane, 1 = low-byte plane, others unused
+                for (int q = 0; q < 4; q++) xv[q] = lds64(xr + q * xunit);
+                // per-segment parameters (all independent of the MMAs: issued up front)
+                constexpr int NSEG = 4 / UPSEG;
+                uint2 sc2[NSEG]; uint32_t zw[NSEG]; uint2 sg[NSEG];
+                #pragma unroll
+                for (int e = 0; e < NSEG; e++) {
+                    const int row = UPSEG == 4 ? 0 : e;
+                    sc2[e] = lds64(sb + sc_lane + row * 256);
+                    zw[e] = lds32(sb + zq_lane + row * 64);
+                    sg[e] = lds64(seg_a + (uint32_t)s * 32u + e * 8 + tok);
                 }
-                int (&aA)[4] = *reinterpret_cast<int (*)[4]>(&ia[0]);
-                int (&aB)[4] = *reinterpret_cast<int (*)[4]>(&ia[4]);
+                // two independent accumulator sets (even / odd units) halve the dependent IMMA chain
+                int ia[2][8];
                 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint32_t M4 = 0x0f0f0f0fu;
                     const uint32_t lo0 = w[q].x & M4, hi0 = (w[q].x >> 4) & M4, lo1 = w[q].y & M4, hi1 = (w[q].y >> 4) & M4;
                     const uint32_t lo2 = w[q].z & M4, hi2 = (w[q].z >> 4) & M4, lo3 = w[q].w & M4, hi3 = (w[q].w >> 4) & M4;
-                    if ((q & (upseg - 1)) == 0) {
+                    const int set = UPSEG == 1 ? 0 : (q & 1);
+                    int (&aA)[4] = *reinterpret_cast<int (*)[4]>(&ia[set][0]);
+                    int (&aB)[4] = *reinterpret_cast<int (*)[4]>(&ia[set][4]);
+                    const bool first = UPSEG == 1 || (q % UPSEG) < 2;        // first unit of this set in the segment
+                    if (first) {
                         imma_z(aA, lo0, lo1, hi0, hi1, xv[q].x, xv[q].y);
                         imma_z(aB, lo2, lo3, hi2, hi3, xv[q].x, xv[q].y);
                     } else {
                         imma(aA, lo0, lo1, hi0, hi1, xv[q].x, xv[q].y);
                         imma(aB, lo2, lo3, hi2, hi3, xv[q].x, xv[q].y);
                     }
-                    if (((q + 1) & (upseg - 1)) == 0) {
+                    if ((q + 1) % UPSEG == 0) {
                         // segment complete: acc += scale * sx * (256 * sum a q + sum b q - zp * sum x_q)
-                        const int seg = q / upseg;
-                        const int row = a.gshift >= 2 ? 0 : seg;
-                        const uint2 sc2 = *reinterpret_cast<const uint2*>(sb + META_SC + row * 256 + lane_col * 2);
-                        const uint32_t zw = *reinterpret_cast<const uint32_t*>(sb + META_ZQ + row * 64 + (lane_col >> 3) * 4);
-                        const uint2 sg = *reinterpret_cast<const uint2*>(segt + (size_t)s * 32 + seg * 8);
-                        const int sxq = (int)sg.x; const float sx = __uint_as_float(sg.y);
-                        const half2 s01 = *reinterpret_cast<const half2*>(&sc2.x), s23 = *reinterpret_cast<const half2*>(&sc2.y);
+                        const int e = q / UPSEG;
+                        const int sxq = (int)sg[e].x; const float sx = __uint_as_float(sg[e].y);
+                        const half2 s01 = *reinterpret_cast<const half2*>(&sc2[e].x), s23 = *reinterpret_cast<const half2*>(&sc2[e].y);
                         const float cs4[4] = {__low2float(s01), __high2float(s01), __low2float(s23), __high2float(s23)};
-                        const uint32_t z4 = zw >> ((lane_col & 4) * 4);
+                        const uint32_t z4 = zw[e] >> zshift;
                         #pragma unroll
                         for (int c = 0; c < 4; c++) {
                             // lane t == 0: D(row g / g+8, col 0 = plane a, col 1 = plane b); column c of this lane = MMA (c >> 1), row half (c & 1)
                             const int jj = (c >> 1) * 4 + (c & 1) * 2;
                             const int zp = (int)((z4 >> (4 * c)) & 0xfu) + 1;
-                            const int val = ia[jj] * 256 + ia[jj + 1] - zp * sxq;
+                            int va = ia[0][jj], vb = ia[0][jj + 1];
+                            if (UPSEG > 1) { va += ia[1][jj]; vb += ia[1][jj + 1]; }
+                            const int val = va * 256 + vb - zp * sxq;
                             acc[c] = fmaf(cs4[c] * sx, (float)val, acc[c]);
                         }
                     }
                 }
+                dep = acc[0] + acc[1] + acc[2] + acc[3];
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + ls * 8);
-            if (ft && fk < 32) { ft[fk * 3 + 2] = gtime(); fk++; }
-            if (++ls == depth) { ls = 0; par ^= 1u; }
+            if (lane == 0) mbar_arrive_dep(empty0 + ls_cur * 8, dep);
             s += 4; while (s >= p.spt) { s -= p.spt; tile++; }
         }
         flush_tile();
+    };
+    auto gemv = [&](const Phase& p, int u0, int u1) {
+        if (rpg == 16) gemv_t(std::integral_constant<int, 4>{}, p, u0, u1);
+        else if (rpg == 8) gemv_t(std::integral_constant<int, 2>{}, p, u0, u1);
+        else gemv_t(std::integral_constant<int, 1>{}, p, u0, u1);
     };
 
     float rm = 0.f;
@@ -532,7 +629,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             stamp(l, 0);
             if (l > 0) zero_share(a.acc_gu, 2 * a.I);
             rm = residual_and_norm(l > 0 ? a.acc_d : nullptr);
-            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(L->ln1, rm));
+            stamp(l, 15);
+            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
             consumer_sync();
             stamp(l, 1);
             gemv(p, u0, u1);
@@ -546,7 +644,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_ATT);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
-            if (l > 0) zero_share(a.acc_d, a.H);
+            if (l > 0 || a.tp_world > 1) zero_share(a.acc_d, a.H);      // its last reader was this layer's QKV prologue
             const int nph = p.tpm;
             const float scale = rsqrtf((float)TILE);
             const int l16 = lane & 15, sub = lane >> 4;
@@ -584,7 +682,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
                     if (lane == 0) { pw[128] = m; pw[129] = lsum; }
                 };
-                for (int u = u0 + (int)((wk - jbase) & 3); u < u1; u += 4) {
+                for (int u = u0 + ((wk - jbase) & 3); u < u1; u += 4) {
                     const int h = u / nph, sg = h - h0, ch = u - h * nph;
                     if (sg != cur) {
                         if (cur >= 0) put_part();
@@ -642,7 +740,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                 for (int sg = 0; sg < nseg; sg++) {
                     const int first = max(u0, (h0 + sg) * nph), last = min(u1, (h0 + sg + 1) * nph);
                     // did this pipeline get a stage of segment sg?  stages of the segment: local indices [first - u0, last - u0)
-                    const int i0 = (first - u0) + (int)((wk - (jbase + (first - u0))) & 3);
+                    const int i0 = (first - u0) + ((wk - (jbase + (first - u0))) & 3);
                     if (i0 >= last - u0) {
                         float* pw = parts + (sg * 17 + warp) * PART_LD;
                         *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -744,7 +842,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             preload_norm(L->ln2, phase_of(a, PH_GU));
             stamp(l, 7);
         }
-        grid_barrier(a.bar, target, (unsigned)G, tid);
+        if (a.tp_world > 1) cross_barrier(a.peer_bar, a.tp_world, a.bar_x, target_x, (unsigned)G, tid);
+        else grid_barrier(a.bar, target, (unsigned)G, tid);
         stamp(l, 8);
 
         // ========================================================= GU ========================================================
@@ -752,10 +851,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const Phase p = phase_of(a, PH_GU);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
             rm = residual_and_norm(a.acc_o);
-            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(L->ln2, rm));
+            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
             consumer_sync();
             stamp(l, 9);
-            gemv(p, u0, u1, l == 2);
+            gemv(p, u0, u1);
             jbase += u1 - u0;
             stamp(l, 10);
         }
@@ -787,7 +886,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             if (l + 1 < a.n_layers) preload_norm(a.layers[l + 1].ln1, phase_of(a, PH_QKV));
             stamp(l, 13);
         }
-        grid_barrier(a.bar, target, (unsigned)G, tid);
+        if (a.tp_world > 1) cross_barrier(a.peer_bar, a.tp_world, a.bar_x, target_x, (unsigned)G, tid);
+        else grid_barrier(a.bar, target, (unsigned)G, tid);
         stamp(l, 14);
     }
 
@@ -813,7 +913,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // stage = 8 chunks of 512 fp16 of the row-major [vocab, H] matrix; the 4 warps of the pipeline take 2 chunks each
         const int cpr = a.H >> 9;                               // chunks per vocabulary row
         const long long nchunks = (long long)a.vocab * cpr;
-        for (int u = u0 + (int)((wk - jbase) & 3); u < u1; u += 4) {
+        for (int u = u0 + ((wk - jbase) & 3); u < u1; u += 4) {
             mbar_wait(full0 + ls * 8, par);
             const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
             const long long c0 = (long long)u * 8 + wn * 2;
@@ -859,11 +959,25 @@ struct exl_decode_plan
     StepArgs args;
     LayerDesc* d_layers = nullptr;
     unsigned char* d_scratch = nullptr;
+    unsigned char* d_shared = nullptr;          // {acc_o, acc_d, cross-barrier counter}: the part peers map through cudaIpc (tensor parallel)
+    size_t shared_o = 0, shared_d = 0, shared_bar = 0;
+    unsigned char* peer_base[8] = {nullptr};    // mapped peer regions (own entry == d_shared)
+    bool peers_ready = false;
     size_t smem = 0;
     int grid = 0;
 };
 
-static int plan_fail(exl_decode_plan* p, int rc) { if (p) { if (p->d_layers) cudaFree(p->d_layers); if (p->d_scratch) cudaFree(p->d_scratch); delete p; } return rc; }
+static int plan_fail(exl_decode_plan* p, int rc)
+{
+    if (p) {
+        for (int r = 0; r < 8; r++) if (p->peer_base[r] && p->peer_base[r] != p->d_shared) cudaIpcCloseMemHandle(p->peer_base[r]);
+        if (p->d_layers) cudaFree(p->d_layers);
+        if (p->d_scratch) cudaFree(p->d_scratch);
+        if (p->d_shared) cudaFree(p->d_shared);
+        delete p;
+    }
+    return rc;
+}
 
 extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan** out)
 {
@@ -912,7 +1026,7 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     a.spt_max = (H > I ? H : I) / TILE; if (HQ / TILE > a.spt_max) a.spt_max = HQ / TILE;
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
-    const size_t fixed = 1024 + (size_t)a.spt_max * (256 + 32) + (size_t)H * 2 + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + 1024 /* static */;
+    const size_t fixed = 1024 + (size_t)a.spt_max * (256 + 32) + (size_t)H * 2 + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + (size_t)H * 2 /* wnorm */ + 1024 /* static */;
     int depth = (int)(((size_t)dev_smem - fixed) / STAGE_STRIDE) / 4;
     if (const char* e = getenv("EXL_DS_DEPTH")) { int v = atoi(e); if (v >= 1 && v < depth) depth = v; }
     if (depth > MAX_DEPTH) depth = MAX_DEPTH;
@@ -933,18 +1047,28 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     // scratch: accumulators | attention partials | barrier
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_qkv = take((size_t)3 * HQ * 4), o_o = take((size_t)H * 4), o_gu = take((size_t)2 * I * 4), o_d = take((size_t)H * 4);
+    const size_t o_qkv = take((size_t)3 * HQ * 4), o_gu = take((size_t)2 * I * 4);
     const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256);
     const bool want_trace = getenv("EXL_DS_TRACE") != nullptr;
-    const size_t o_trace = want_trace ? take((size_t)p->grid * (TRACE_LAYERS * 16 + 96) * 8) : 0;
-    if (cudaMalloc(&p->d_scratch, off) != cudaSuccess || cudaMalloc(&p->d_layers, sizeof(LayerDesc) * L.size()) != cudaSuccess)
+    const size_t o_trace = want_trace ? take((size_t)p->grid * TRACE_LAYERS * 16 * 8) : 0;
+    p->shared_o = 0; p->shared_d = ((size_t)H * 4 + 255) & ~(size_t)255; p->shared_bar = 2 * p->shared_d;
+    const size_t shared_bytes = p->shared_bar + 256;
+    if (cudaMalloc(&p->d_scratch, off) != cudaSuccess || cudaMalloc(&p->d_layers, sizeof(LayerDesc) * L.size()) != cudaSuccess ||
+        cudaMalloc(&p->d_shared, shared_bytes) != cudaSuccess)
         return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: cudaMalloc failed"));
-    if (cudaMemset(p->d_scratch, 0, off) != cudaSuccess ||
+    if (cudaMemset(p->d_scratch, 0, off) != cudaSuccess || cudaMemset(p->d_shared, 0, shared_bytes) != cudaSuccess ||
         cudaMemcpy(p->d_layers, L.data(), sizeof(LayerDesc) * L.size(), cudaMemcpyHostToDevice) != cudaSuccess)
         return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: upload failed"));
     a.layers = p->d_layers;
-    a.acc_qkv = (float*)(p->d_scratch + o_qkv); a.acc_o = (float*)(p->d_scratch + o_o); a.acc_gu = (float*)(p->d_scratch + o_gu);
-    a.acc_d = (float*)(p->d_scratch + o_d); a.att_part = (float*)(p->d_scratch + o_att); a.bar = (unsigned long long*)(p->d_scratch + o_bar);
+    a.acc_qkv = (float*)(p->d_scratch + o_qkv); a.acc_gu = (float*)(p->d_scratch + o_gu);
+    a.acc_o = (float*)(p->d_shared + p->shared_o); a.acc_d = (float*)(p->d_shared + p->shared_d);
+    a.bar_x = (unsigned long long*)(p->d_shared + p->shared_bar);
+    a.tp_rank = d->tp_world > 1 ? d->tp_rank : 0; a.tp_world = d->tp_world > 1 ? d->tp_world : 1;
+    if (a.tp_world > 8 || a.tp_rank < 0 || a.tp_rank >= a.tp_world) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: bad tensor-parallel rank %d / world %d", d->tp_rank, d->tp_world));
+    p->peer_base[a.tp_rank] = p->d_shared;
+    a.peer_o[a.tp_rank] = a.acc_o; a.peer_d[a.tp_rank] = a.acc_d; a.peer_bar[a.tp_rank] = a.bar_x;
+    p->peers_ready = a.tp_world == 1;
+    a.att_part = (float*)(p->d_scratch + o_att); a.bar = (unsigned long long*)(p->d_scratch + o_bar);
     if (const char* ed = getenv("EXL_DS_DEBUG")) a.debug = atoi(ed);
     a.trace = want_trace ? (unsigned long long*)(p->d_scratch + o_trace) : nullptr;
     *out = p;
@@ -960,6 +1084,40 @@ extern "C" int exl_decode_plan_destroy(exl_decode_plan* p)
     return EXL_OK;
 }
 
+// Tensor parallel: the region peers reduce into is exported as a cudaIpc handle (64 bytes) ...
+extern "C" int exl_decode_plan_ipc_export(exl_decode_plan* p, void* handle64)
+{
+    if (!p || !handle64) return exl_set_err(EXL_ERR_STATE, "decode_plan_ipc_export: NULL argument");
+    DeviceGuard guard(p->device);
+    cudaIpcMemHandle_t h;
+    EXL_CUDA_TRY(cudaIpcGetMemHandle(&h, p->d_shared));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    memcpy(handle64, &h, 64);
+    return EXL_OK;
+}
+
+// ... and every rank imports all ranks' handles (world x 64 bytes, in rank order; its own entry is ignored) before the first step.
+extern "C" int exl_decode_plan_ipc_import(exl_decode_plan* p, const void* handles, int world)
+{
+    if (!p || !handles) return exl_set_err(EXL_ERR_STATE, "decode_plan_ipc_import: NULL argument");
+    if (world != p->args.tp_world) return exl_set_err(EXL_ERR_ARG, "decode_plan_ipc_import: %d handles for a world of %d", world, p->args.tp_world);
+    DeviceGuard guard(p->device);
+    StepArgs& a = p->args;
+    for (int r = 0; r < world; r++) {
+        if (r == a.tp_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)handles + (size_t)r * 64, 64);
+        void* base = nullptr;
+        EXL_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_base[r] = (unsigned char*)base;
+        a.peer_o[r] = (float*)(p->peer_base[r] + p->shared_o);
+        a.peer_d[r] = (float*)(p->peer_base[r] + p->shared_d);
+        a.peer_bar[r] = (unsigned long long*)(p->peer_base[r] + p->shared_bar);
+    }
+    p->peers_ready = true;
+    return EXL_OK;
+}
+
 extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step)
 {
     if (!p) return exl_set_err(EXL_ERR_STATE, "decode_plan_info: NULL plan");
@@ -972,7 +1130,7 @@ extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ri
 extern "C" int exl_decode_plan_trace(exl_decode_plan* p, unsigned long long* out_host, int64_t capacity)
 {
     if (!p || !p->args.trace) return exl_set_err(EXL_ERR_STATE, "decode_plan_trace: plan has no trace buffer (set EXL_DS_TRACE=1 before creating it)");
-    const int64_t n = (int64_t)p->grid * (TRACE_LAYERS * 16 + 96);
+    const int64_t n = (int64_t)p->grid * TRACE_LAYERS * 16;
     if (capacity < n) return exl_set_err(EXL_ERR_ARG, "decode_plan_trace: need room for %lld values", (long long)n);
     DeviceGuard guard(p->device);
     EXL_CUDA_TRY(cudaMemcpy(out_host, p->args.trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
@@ -985,6 +1143,7 @@ extern "C" int exl_decode_step(exl_decode_plan* p, const void* x_in, int past_le
     if (!x_in) return exl_set_err(EXL_ERR_ARG, "decode_step: x_in is NULL");
     if (past_len < 0 || past_len >= p->args.max_seq) return exl_set_err(EXL_ERR_ARG, "decode_step: past_len %d outside the cache (max_seq %d)", past_len, p->args.max_seq);
     if (p->args.lm_head && !logits) return exl_set_err(EXL_ERR_ARG, "decode_step: the plan has an lm_head, logits must be given");
+    if (!p->peers_ready) return exl_set_err(EXL_ERR_STATE, "decode_step: tensor-parallel plan: call exl_decode_plan_ipc_import first");
     DeviceGuard guard(p->device);
     StepArgs a = p->args;
     a.x_in = (const half*)x_in; a.x_out = (half*)x_out; a.logits = (float*)logits; a.past_len = past_len;

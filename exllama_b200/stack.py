@@ -168,13 +168,19 @@ class DecodeStack:
     def make_plan(self, with_head=True):
         """Build the exl_decode_plan over this stack's handles, norms, caches and tables (borrowed)."""
         from . import capi
-        if self.tp_size != 1:
-            raise NotImplementedError("the fused decode step is single-GPU")
         hs = [[L.q.q4, L.k.q4, L.v.q4, L.o.q4, L.gate.q4, L.up.q4, L.down.q4] for L in self.layers]
         head = self.lm_head if with_head else None
         self.dplan = capi.DecodePlan(hs, [L.ln1 for L in self.layers], [L.ln2 for L in self.layers], self.key_cache, self.value_cache,
                                     self.sin, self.cos, self.local_heads, self.shape.head_dim, self.max_seq, self.shape.eps,
-                                    final_norm=self.norm if head is not None else None, lm_head=head)
+                                    final_norm=self.norm if head is not None else None, lm_head=head,
+                                    tp_rank=self.tp_rank, tp_world=self.tp_size)
+        if self.tp_size > 1:
+            # exchange the cudaIpc handles of the regions the peers reduce into (acc_o, acc_d, cross-barrier counter)
+            import torch.distributed as dist
+            handles = [None] * self.tp_size
+            dist.all_gather_object(handles, self.dplan.ipc_export(), group=self.tp_group)
+            self.dplan.ipc_import(handles)
+            dist.barrier(self.tp_group)
         self._plan_xout = torch.empty(self.shape.hidden, dtype=torch.float16, device=self.device)
         self._plan_logits = torch.empty((1, self.shape.vocab), dtype=torch.float32, device=self.device) if head is not None else None
         return self.dplan

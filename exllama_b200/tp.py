@@ -170,9 +170,14 @@ def row_parallel_residual(ext, x, inp, q4, rank, group):
 def mlp_tp(ext, cuda_ext, x, L, eps, rank, group):
     """Tensor-parallel MLP block: the same two fused launches as the single-GPU q4_mlp ([norm -> gate,up -> silu*mul],
     [down]) on this rank's column / row shards, then ONE all-reduce of the [M, hidden] partial."""
-    if _fused_ready and x.shape[0] <= 8:
-        ext.q4_mlp_ar(x, L.ln2, eps, L.gate.q4, L.up.q4, L.down.q4)
-        return
+    if _fused_ready and x.shape[0] <= 8 and not getattr(L, "_no_fused_mlp", False):
+        try:
+            ext.q4_mlp_ar(x, L.ln2, eps, L.gate.q4, L.up.q4, L.down.q4)
+            return
+        except RuntimeError:
+            # act-order (gate / up carry different x_maps) or LoRA: the single-launch configuration does not apply; the
+            # entry point refuses BEFORE launching anything, so falling back to the two-step variant + NCCL is safe
+            L._no_fused_mlp = True
     ext.q4_mlp_tp(x, L.ln2, eps, L.gate.q4, L.up.q4, L.down.q4, rank == 0)
     all_reduce(x, group)
 
@@ -202,3 +207,9 @@ def init_fused_allreduce(ext, device_index, group=None):
 
 def fused_ready():
     return _fused_ready
+
+
+def reset_fused_allreduce():
+    """Call after ext.cleanup(): the workspace behind the fused all-reduce is gone."""
+    global _fused_ready
+    _fused_ready = False

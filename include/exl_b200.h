@@ -175,10 +175,19 @@ typedef struct exl_decode_desc {
     const void* sin; const void* cos;    /* half [max_seq_len, head_dim] (model.py:864-877) */
     const void* final_norm;              /* half [hidden] or NULL */
     const void* lm_head;                 /* half [vocab, hidden] (nn.Linear weight, model.py:845-846) or NULL: no head */
+    /* tensor parallel (0 / 1 = single GPU): this rank's column shards of q, k, v, gate, up (num_heads = LOCAL heads) and
+       row shards of o, down; norms, tables, x and the head replicated.  The row-parallel partials are reduced into every rank's
+       accumulator over NVLink inside the same kernel (peer-memory atomics + a cross-GPU barrier): no separate collective. */
+    int tp_rank, tp_world;
 } exl_decode_desc;
 
 int exl_decode_plan_create(const exl_decode_desc* desc, exl_decode_plan** out_plan);
 int exl_decode_plan_destroy(exl_decode_plan* plan);
+/* Tensor parallel set-up: export this rank's 64-byte cudaIpc handle, exchange (e.g. through torch.distributed), import all of
+   them (world x 64 bytes in rank order) on every rank before the first exl_decode_step; every rank must then call
+   exl_decode_step for the same token at about the same time (a rank that waits longer than 4 s for its peers traps). */
+int exl_decode_plan_ipc_export(exl_decode_plan* plan, void* handle64);
+int exl_decode_plan_ipc_import(exl_decode_plan* plan, const void* handles, int world);
 int exl_decode_plan_info(const exl_decode_plan* plan, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step);
 
 /* Bring-up aid: with EXL_DS_TRACE=1 in the environment when the plan is created, every CTA stamps %globaltimer at its phase

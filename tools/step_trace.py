@@ -36,16 +36,11 @@ for i, n in enumerate(names):
     d = (t[:, i + 1] - t[:, i]) / 1e3
     rows.append({"seg": n, "med_us": round(float(np.median(d)), 2), "min_us": round(float(d.min()), 2), "max_us": round(float(d.max()), 2),
                  "end_med_us": round(float(np.median(t[:, i + 1])) / 1e3, 2)})
+qkv_resnorm = float(np.median(tr[:, L, 15] - tr[:, L, 0])) / 1e3
 layer_us = float(np.median(tr[:, L, 14] - tr[:, L, 0])) / 1e3
 print(json.dumps({"debug": os.environ.get("EXL_DS_DEBUG"), "nst": os.environ.get("EXL_DS_DEPTH"), "ctx": args.ctx, "layers": args.layers,
-                  "ms_per_step": round(ms, 4), "layer_us": round(layer_us, 2), "plan": st.dplan.info()}))
+                  "ms_per_step": round(ms, 4), "layer_us": round(layer_us, 2), "qkv_pro_residual_norm_us": round(qkv_resnorm, 2), "plan": st.dplan.info()}))
 for r in rows:
     print(json.dumps(r))
 
-ft = st.dplan.fine_trace.astype(np.int64)
-for c in (0, 73, 147):
-    f = ft[c]; n = int((f[:, 2] > 0).sum())
-    if n == 0: continue
-    t0 = f[0, 0]
-    print(json.dumps({"cta": c, "stages": n, "wait_us": [round((f[k, 1] - f[k, 0]) / 1e3, 2) for k in range(n)],
-                      "work_us": [round((f[k, 2] - f[k, 1]) / 1e3, 2) for k in range(n)], "end_us": round((f[n - 1, 2] - t0) / 1e3, 2)}))
+
