@@ -277,10 +277,10 @@ class DecodePlan:
         check(lib().exl_decode_step(self.handle, _ptr(x_in), past_len, _ptr(x_out), _ptr(logits), _stream()))
 
     def trace(self):
-        """[grid, 4 layers, 16 events] globaltimer stamps (ns) of the last launch (EXL_DS_TRACE=1 at creation)."""
+        """[grid, 4 layers, 24 events] globaltimer stamps (ns) of the last launch (EXL_DS_TRACE=1 at creation)."""
         import numpy as np
         g = self.info()["grid"]
-        out = np.zeros((g, 4, 16), dtype=np.uint64)
+        out = np.zeros((g, 4, 24), dtype=np.uint64)
         check(lib().exl_decode_plan_trace(self.handle, out.ctypes.data_as(vp), out.size))
         return out
 

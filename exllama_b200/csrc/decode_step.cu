@@ -82,13 +82,17 @@ struct StepArgs
     float* acc_qkv; float* acc_o; float* acc_gu; float* acc_d;                 // fp32 phase accumulators in L2
     float* att_part; int att_slots;    // [heads][att_slots][PART_LD]
     unsigned long long* bar;           // grid barrier: monotonic arrival counter (this GPU's CTAs only)
-    // tensor parallel (world > 1): the row-parallel projections (o_proj, down_proj) add their partials into EVERY rank's accumulator
-    // over NVLink peer memory, and the barrier that follows them is a cross-GPU barrier (every CTA of every rank arrives on every
-    // rank's cross counter) -- the all-reduce is the split-K reduction, there is no separate collective.
+    // tensor parallel (world > 1): after a row-parallel projection (o_proj, down_proj) every rank's partial [H] vector -- already
+    // reduced over its own CTAs in L2 -- is stored straight into slot [rank] of EVERY peer over NVLink as 8-byte {value, epoch}
+    // pairs (posted writes, H / grid elements per CTA and peer).  There is no cross-GPU barrier and no system-scope fence: the next
+    // prologue polls each pair until its epoch matches (an 8-byte store is single-copy atomic, as in NCCL's LL protocol), and the
+    // slots cannot be overwritten early because a peer's next partial causally depends on this rank's next one.  One-shot
+    // all-reduce inside the kernel: no separate collective, no host involvement, CUDA-graph replayable (the epoch comes from a
+    // device-side launch counter).
     int tp_rank, tp_world;
-    float* peer_o[8]; float* peer_d[8];          // acc_o / acc_d of every rank, mapped here (own entry == acc_o / acc_d)
-    unsigned long long* peer_bar[8];             // cross-barrier counter of every rank
-    unsigned long long* bar_x;                   // own cross-barrier counter (== peer_bar[tp_rank])
+    uint2* push_o[8]; uint2* push_d[8];          // where THIS rank's partial goes on rank r: slots_o / slots_d of rank r, row tp_rank
+    const uint2* slots_o; const uint2* slots_d;  // own receive slots [world][H] of {float bits, epoch}
+    unsigned* launch_ctr;                        // launches completed so far (all ranks run the same number)
     int debug;                         // EXL_DS_DEBUG bitmask (bring-up experiments): 1 skip GEMV math, 2 skip attention math, 4 skip head math
     unsigned long long* trace;         // optional [G][TRACE_LAYERS][16] globaltimer stamps of CTA thread 0 (EXL_DS_TRACE=1), else NULL
 };
@@ -217,15 +221,15 @@ __device__ __forceinline__ int share_lo(long long n, int c, int G) { return (int
 // the CTA whose share contains item u (inverse of share_lo)
 __device__ __forceinline__ int cta_of(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
 
-struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; float* const* peers; };     // tpm: tiles per matrix (ATT: units per head)
+struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; };     // tpm: tiles per matrix (ATT: units per head)
 
 __device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
 {
-    Phase p; p.kind = kind; p.acc = nullptr; p.peers = nullptr; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
+    Phase p; p.kind = kind; p.acc = nullptr; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
     if (kind == PH_QKV)       { p.spt = a.H / TILE;  p.N = a.HQ; p.nmat = 3; p.mat0 = 0; p.acc = a.acc_qkv; }
-    else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; p.peers = a.tp_world > 1 ? a.peer_o : nullptr; }
+    else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; }
     else if (kind == PH_GU)   { p.spt = a.H / TILE;  p.N = a.I;  p.nmat = 2; p.mat0 = 4; p.acc = a.acc_gu; }
-    else if (kind == PH_DOWN) { p.spt = a.I / TILE;  p.N = a.H;  p.nmat = 1; p.mat0 = 6; p.acc = a.acc_d; p.peers = a.tp_world > 1 ? a.peer_d : nullptr; }
+    else if (kind == PH_DOWN) { p.spt = a.I / TILE;  p.N = a.H;  p.nmat = 1; p.mat0 = 6; p.acc = a.acc_d; }
     if (kind == PH_ATT) {
         const int nch = (a.past_len + 15) >> 4;
         p.tpm = nch > 0 ? nch : 1;                          // units per head (one empty unit when there is no history)
@@ -259,27 +263,6 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
         }
     }
     target += nctas;
-    consumer_sync();
-}
-
-// Cross-GPU barrier (tensor parallel): every CTA of every rank adds 1 to the cross counter of EVERY rank with release semantics at
-// system scope -- which also orders this CTA's earlier peer-memory reductions before the arrival -- and polls its own counter.
-__device__ __forceinline__ void cross_barrier(unsigned long long* const* peer_bar, int world, unsigned long long* own, unsigned long long& target,
-                                              unsigned nctas, int tid)
-{
-    consumer_sync();
-    if (tid == 0) {
-        for (int r = 0; r < world; r++)
-            asm volatile("red.release.sys.global.add.u64 [%0], 1;" :: "l"(peer_bar[r]) : "memory");
-        unsigned long long v;
-        const unsigned long long t0 = gtime();
-        unsigned i = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(own) : "memory");
-            if ((++i & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
-        } while (v < target);
-    }
-    target += (unsigned long long)nctas * world;
     consumer_sync();
 }
 
@@ -394,21 +377,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     const uint32_t ring_a = smem_u32(ring) + (uint32_t)wk * depth * STAGE_STRIDE;
     const uint32_t full0 = smem_u32(&full_bar[wk * depth]), empty0 = smem_u32(&empty_bar[wk * depth]);
     int ls = 0; uint32_t par = 0;                        // this pipeline's ring position (every warp of the pipeline visits every stage)
-    auto stamp = [&](int l, int ev) { if (a.trace && tid == 0 && l < TRACE_LAYERS) a.trace[((size_t)cta * TRACE_LAYERS + l) * 16 + ev] = gtime(); };
+    auto stamp = [&](int l, int ev) { if (a.trace && tid == 0 && l < TRACE_LAYERS) a.trace[((size_t)cta * TRACE_LAYERS + l) * 24 + ev] = gtime(); };
     int jbase = 0;                                       // stages this CTA has been through (same count as the producers)
     if (tid == 0) {
         unsigned long long v;
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
         s_base = v - v % (unsigned long long)G;          // at most G - 1 CTAs of THIS launch can have arrived already
-        if (a.tp_world > 1) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar_x) : "memory");
-            const unsigned long long gw = (unsigned long long)G * a.tp_world;
-            s_base_x = v - v % gw;                       // a faster rank can be at most one cross barrier (< G * world arrivals) ahead
-        }
+        s_base_x = a.tp_world > 1 ? (unsigned long long)__ldcg(a.launch_ctr) : 0ull;
     }
     consumer_sync();
     unsigned long long target = s_base + (unsigned long long)G;
-    unsigned long long target_x = a.tp_world > 1 ? s_base_x + (unsigned long long)G * a.tp_world : 0ull;
+    const unsigned epoch0 = (unsigned)s_base_x * (unsigned)(2 * a.n_layers) + 1u;      // epoch of (layer l, o / down) = epoch0 + 2 l + {0, 1}
 
     auto zero_share = [&](float* buf, int n) {            // this CTA's share of a float buffer (n % 4 == 0)
         const int lo = share_lo(n >> 2, cta, G), hi = share_lo(n >> 2, cta + 1, G);
@@ -416,10 +395,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
 
     // ---- launch start: all accumulators and the logits to zero (robust against an aborted previous launch), then barrier ----
-    // (tensor parallel: acc_o / acc_d also receive the peers' partials, possibly before this rank has even started -- they are kept
-    //  clean by the in-kernel schedule alone: acc_o is zeroed in every DOWN phase, acc_d in every ATT phase)
-    zero_share(a.acc_qkv, 3 * a.HQ); zero_share(a.acc_gu, 2 * a.I);
-    if (a.tp_world == 1) { zero_share(a.acc_o, a.H); zero_share(a.acc_d, a.H); }
+    zero_share(a.acc_qkv, 3 * a.HQ); zero_share(a.acc_o, a.H); zero_share(a.acc_gu, 2 * a.I); zero_share(a.acc_d, a.H);
     if (a.logits) zero_share(a.logits, a.vocab);
     for (int i = tid; i < a.H / 8; i += DS_CONSUMERS)
         reinterpret_cast<uint4*>(xres)[i] = __ldg(reinterpret_cast<const uint4*>(a.x_in) + i);
@@ -440,16 +416,46 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
     preload_norm(a.layers[0].ln1, phase_of(a, PH_QKV));
     grid_barrier(a.bar, target, (unsigned)G, tid);
+    if (a.tp_world > 1 && cta == 0 && tid == 0) *a.launch_ctr = (unsigned)s_base_x + 1u;      // every CTA has read it (it is past the barrier)
 
     // ---- residual add (fp16(x + fp32 delta), the rounding point of q4_matmul's no_zero epilogue) + row factor of the RMS norm ----
-    auto residual_and_norm = [&](const float* delta) -> float {
+    auto residual_and_norm = [&](const float* delta, const uint2* slots = nullptr, unsigned epoch = 0u) -> float {
         asm volatile("cp.async.wait_all;" ::: "memory");
         float ss = 0.f;
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
             uint4 xv = reinterpret_cast<uint4*>(xres)[i];
             half2* h = reinterpret_cast<half2*>(&xv);
             if (delta) {
-                const float4 d0 = ldcg4(delta + i * 8), d1 = ldcg4(delta + i * 8 + 4);
+                const float4 own0 = ldcg4(delta + i * 8), own1 = ldcg4(delta + i * 8 + 4);
+                float4 d0 = own0, d1 = own1;
+                if (slots) {
+                    // tensor parallel: the sum over ALL ranks' partials in rank order (bitwise identical on every rank); the peers'
+                    // partials sit in this rank's slots as {value, epoch} pairs, polled until the epoch of this (layer, phase) shows up
+                    d0 = make_float4(0.f, 0.f, 0.f, 0.f); d1 = d0;
+                    for (int r = 0; r < a.tp_world; r++) {
+                        float e[8];
+                        if (r == a.tp_rank) {
+                            e[0] = own0.x; e[1] = own0.y; e[2] = own0.z; e[3] = own0.w; e[4] = own1.x; e[5] = own1.y; e[6] = own1.z; e[7] = own1.w;
+                        } else {
+                            const uint4* sp = reinterpret_cast<const uint4*>(slots + (size_t)r * a.H + i * 8);
+                            #pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                uint4 v;
+                                asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(sp + q) : "memory");
+                                if (v.y != epoch || v.w != epoch) {
+                                    const unsigned long long t0 = gtime();
+                                    unsigned spin = 0;
+                                    do {
+                                        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(sp + q) : "memory");
+                                        if ((++spin & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
+                                    } while (v.y != epoch || v.w != epoch);
+                                }
+                                e[2 * q] = __uint_as_float(v.x); e[2 * q + 1] = __uint_as_float(v.z);
+                            }
+                        }
+                        d0.x += e[0]; d0.y += e[1]; d0.z += e[2]; d0.w += e[3]; d1.x += e[4]; d1.y += e[5]; d1.z += e[6]; d1.w += e[7];
+                    }
+                }
                 float2 f;
                 f = __half22float2(h[0]); h[0] = __floats2half2_rn(f.x + d0.x, f.y + d0.y);
                 f = __half22float2(h[1]); h[1] = __floats2half2_rn(f.x + d0.z, f.y + d0.w);
@@ -516,17 +522,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         auto flush_tile = [&]() {
             if (t == 0) {
                 const int mi = cur_tile / p.tpm, col0 = (cur_tile - mi * p.tpm) * TILE;
-                const size_t off = (size_t)mi * p.N + col0 + lane_col;
-                red_add_v4(p.acc + off, acc[0], acc[1], acc[2], acc[3]);
-                if (p.peers) {
-                    // row-parallel projection of a tensor-parallel layer: the same partial into every peer's accumulator (NVLink)
-                    for (int r = 0; r < a.tp_world; r++) {
-                        if (r == a.tp_rank) continue;
-                        float* d = p.peers[r] + off;
-                        #pragma unroll
-                        for (int c = 0; c < 4; c++) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(d + c), "f"(acc[c]) : "memory");
-                    }
-                }
+                red_add_v4(p.acc + (size_t)mi * p.N + col0 + lane_col, acc[0], acc[1], acc[2], acc[3]);
             }
             acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         };
@@ -618,6 +614,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         else gemv_t(std::integral_constant<int, 1>{}, p, u0, u1);
     };
 
+    // tensor parallel: after the local barrier, this CTA's share of the rank's reduced partial goes into every peer's slot [tp_rank]
+    // as {value, epoch} pairs (8-byte stores; two pairs per 16-byte store are fine: each pair is validated on its own)
+    auto push_partial = [&](const float* acc, uint2* const* push, unsigned epoch, int l, int ev) {
+        grid_barrier(a.bar, target, (unsigned)G, tid);                     // the rank's partial is complete in L2
+        stamp(l, ev);
+        const int lo = share_lo(a.H >> 1, cta, G), n2 = share_lo(a.H >> 1, cta + 1, G) - lo;      // in units of 2 floats
+        for (int i = tid; i < n2 * (a.tp_world - 1); i += DS_CONSUMERS) {
+            int r = i / n2; const int j = i - r * n2;
+            if (r >= a.tp_rank) r++;
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + lo + j);
+            uint4 o = make_uint4(__float_as_uint(v.x), epoch, __float_as_uint(v.y), epoch);
+            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(reinterpret_cast<uint4*>(push[r]) + lo + j), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+        stamp(l, ev + 1);
+    };
+
     float rm = 0.f;
     #pragma unroll 1
     for (int l = 0; l < a.n_layers; l++) {
@@ -628,7 +640,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
             stamp(l, 0);
             if (l > 0) zero_share(a.acc_gu, 2 * a.I);
-            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr);
+            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
             stamp(l, 15);
             if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
             consumer_sync();
@@ -644,7 +656,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_ATT);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
-            if (l > 0 || a.tp_world > 1) zero_share(a.acc_d, a.H);      // its last reader was this layer's QKV prologue
+            if (l > 0) zero_share(a.acc_d, a.H);
             const int nph = p.tpm;
             const float scale = rsqrtf((float)TILE);
             const int l16 = lane & 15, sub = lane >> 4;
@@ -842,7 +854,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             preload_norm(L->ln2, phase_of(a, PH_GU));
             stamp(l, 7);
         }
-        if (a.tp_world > 1) cross_barrier(a.peer_bar, a.tp_world, a.bar_x, target_x, (unsigned)G, tid);
+        if (a.tp_world > 1) push_partial(a.acc_o, a.push_o, epoch0 + 2u * l, l, 16);
         else grid_barrier(a.bar, target, (unsigned)G, tid);
         stamp(l, 8);
 
@@ -850,7 +862,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_GU);
             const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
-            rm = residual_and_norm(a.acc_o);
+            rm = residual_and_norm(a.acc_o, a.tp_world > 1 ? a.slots_o : nullptr, epoch0 + 2u * l);
             if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
             consumer_sync();
             stamp(l, 9);
@@ -886,13 +898,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             if (l + 1 < a.n_layers) preload_norm(a.layers[l + 1].ln1, phase_of(a, PH_QKV));
             stamp(l, 13);
         }
-        if (a.tp_world > 1) cross_barrier(a.peer_bar, a.tp_world, a.bar_x, target_x, (unsigned)G, tid);
+        if (a.tp_world > 1) push_partial(a.acc_d, a.push_d, epoch0 + 2u * l + 1u, l, 18);
         else grid_barrier(a.bar, target, (unsigned)G, tid);
         stamp(l, 14);
     }
 
     // ========================================================= HEAD ==========================================================
-    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr);
+    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && a.n_layers > 0) ? a.slots_d : nullptr, epoch0 + 2u * (a.n_layers - 1) + 1u);
     if (a.x_out && cta == 0)
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
     if (a.lm_head) {
@@ -959,7 +971,7 @@ struct exl_decode_plan
     StepArgs args;
     LayerDesc* d_layers = nullptr;
     unsigned char* d_scratch = nullptr;
-    unsigned char* d_shared = nullptr;          // {acc_o, acc_d, cross-barrier counter}: the part peers map through cudaIpc (tensor parallel)
+    unsigned char* d_shared = nullptr;          // {slots_o[world][H], slots_d[world][H]} of {value, epoch} pairs: the part peers map through cudaIpc
     size_t shared_o = 0, shared_d = 0, shared_bar = 0;
     unsigned char* peer_base[8] = {nullptr};    // mapped peer regions (own entry == d_shared)
     bool peers_ready = false;
@@ -1047,11 +1059,12 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     // scratch: accumulators | attention partials | barrier
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_qkv = take((size_t)3 * HQ * 4), o_gu = take((size_t)2 * I * 4);
+    const size_t o_qkv = take((size_t)3 * HQ * 4), o_o = take((size_t)H * 4), o_gu = take((size_t)2 * I * 4), o_d = take((size_t)H * 4);
     const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256);
     const bool want_trace = getenv("EXL_DS_TRACE") != nullptr;
-    const size_t o_trace = want_trace ? take((size_t)p->grid * TRACE_LAYERS * 16 * 8) : 0;
-    p->shared_o = 0; p->shared_d = ((size_t)H * 4 + 255) & ~(size_t)255; p->shared_bar = 2 * p->shared_d;
+    const size_t o_trace = want_trace ? take((size_t)p->grid * TRACE_LAYERS * 24 * 8) : 0;
+    const int W = d->tp_world > 1 ? d->tp_world : 1;
+    p->shared_o = 0; p->shared_d = (((size_t)W * H * 8) + 255) & ~(size_t)255; p->shared_bar = 2 * p->shared_d;
     const size_t shared_bytes = p->shared_bar + 256;
     if (cudaMalloc(&p->d_scratch, off) != cudaSuccess || cudaMalloc(&p->d_layers, sizeof(LayerDesc) * L.size()) != cudaSuccess ||
         cudaMalloc(&p->d_shared, shared_bytes) != cudaSuccess)
@@ -1061,12 +1074,13 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
         return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: upload failed"));
     a.layers = p->d_layers;
     a.acc_qkv = (float*)(p->d_scratch + o_qkv); a.acc_gu = (float*)(p->d_scratch + o_gu);
-    a.acc_o = (float*)(p->d_shared + p->shared_o); a.acc_d = (float*)(p->d_shared + p->shared_d);
-    a.bar_x = (unsigned long long*)(p->d_shared + p->shared_bar);
+    a.acc_o = (float*)(p->d_scratch + o_o); a.acc_d = (float*)(p->d_scratch + o_d);
+    a.slots_o = (const uint2*)(p->d_shared + p->shared_o); a.slots_d = (const uint2*)(p->d_shared + p->shared_d);
+    a.launch_ctr = (unsigned*)(p->d_scratch + o_bar + 64);
     a.tp_rank = d->tp_world > 1 ? d->tp_rank : 0; a.tp_world = d->tp_world > 1 ? d->tp_world : 1;
     if (a.tp_world > 8 || a.tp_rank < 0 || a.tp_rank >= a.tp_world) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: bad tensor-parallel rank %d / world %d", d->tp_rank, d->tp_world));
     p->peer_base[a.tp_rank] = p->d_shared;
-    a.peer_o[a.tp_rank] = a.acc_o; a.peer_d[a.tp_rank] = a.acc_d; a.peer_bar[a.tp_rank] = a.bar_x;
+    a.push_o[a.tp_rank] = nullptr; a.push_d[a.tp_rank] = nullptr;
     p->peers_ready = a.tp_world == 1;
     a.att_part = (float*)(p->d_scratch + o_att); a.bar = (unsigned long long*)(p->d_scratch + o_bar);
     if (const char* ed = getenv("EXL_DS_DEBUG")) a.debug = atoi(ed);
@@ -1110,9 +1124,8 @@ extern "C" int exl_decode_plan_ipc_import(exl_decode_plan* p, const void* handle
         void* base = nullptr;
         EXL_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
         p->peer_base[r] = (unsigned char*)base;
-        a.peer_o[r] = (float*)(p->peer_base[r] + p->shared_o);
-        a.peer_d[r] = (float*)(p->peer_base[r] + p->shared_d);
-        a.peer_bar[r] = (unsigned long long*)(p->peer_base[r] + p->shared_bar);
+        a.push_o[r] = (uint2*)(p->peer_base[r] + p->shared_o) + (size_t)a.tp_rank * a.H;
+        a.push_d[r] = (uint2*)(p->peer_base[r] + p->shared_d) + (size_t)a.tp_rank * a.H;
     }
     p->peers_ready = true;
     return EXL_OK;
@@ -1130,7 +1143,7 @@ extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ri
 extern "C" int exl_decode_plan_trace(exl_decode_plan* p, unsigned long long* out_host, int64_t capacity)
 {
     if (!p || !p->args.trace) return exl_set_err(EXL_ERR_STATE, "decode_plan_trace: plan has no trace buffer (set EXL_DS_TRACE=1 before creating it)");
-    const int64_t n = (int64_t)p->grid * TRACE_LAYERS * 16;
+    const int64_t n = (int64_t)p->grid * TRACE_LAYERS * 24;
     if (capacity < n) return exl_set_err(EXL_ERR_ARG, "decode_plan_trace: need room for %lld values", (long long)n);
     DeviceGuard guard(p->device);
     EXL_CUDA_TRY(cudaMemcpy(out_host, p->args.trace, (size_t)n * 8, cudaMemcpyDeviceToHost));

@@ -81,7 +81,9 @@ class DecodeStack:
         hq = self.local_heads * shape.head_dim
         il = plan.inter_cols[tp_rank][1] - plan.inter_cols[tp_rank][0]
         gen = torch.Generator(device=self.device)
-        gen.manual_seed(seed * 1000 + tp_rank)
+        gen.manual_seed(seed * 1000 + tp_rank)                 # this rank's shards
+        rep = torch.Generator(device=self.device)
+        rep.manual_seed(seed * 1000 + 977)                     # replicated tensors (norms, head): identical on every rank
         with torch.cuda.device(self.device):
             ext.set_tuning_params(8, 2, 8, False, False, False, False, False, False)
             self.layers = []
@@ -92,15 +94,15 @@ class DecodeStack:
                 L.o = mk(hq, h)
                 L.gate, L.up = mk(h, il), mk(h, il)
                 L.down = mk(il, h)
-                L.ln1 = (1 + 0.05 * torch.randn(h, device=self.device, generator=gen)).half()
-                L.ln2 = (1 + 0.05 * torch.randn(h, device=self.device, generator=gen)).half()
+                L.ln1 = (1 + 0.05 * torch.randn(h, device=self.device, generator=rep)).half()
+                L.ln2 = (1 + 0.05 * torch.randn(h, device=self.device, generator=rep)).half()
                 self.layers.append(L)
             if act_order and tp_size > 1:
                 g0 = torch.Generator(device="cpu"); g0.manual_seed(seed * 7919 + 13)            # same on every rank
                 perm = torch.randperm(h, generator=g0)
                 self.o_rows = perm[tp_rank * hq:(tp_rank + 1) * hq].sort().values.to(self.device)
-            self.norm = (1 + 0.05 * torch.randn(h, device=self.device, generator=gen)).half()
-            self.lm_head = (torch.randn((shape.vocab, h), device=self.device, generator=gen) * 0.02).half() if with_head else None
+            self.norm = (1 + 0.05 * torch.randn(h, device=self.device, generator=rep)).half()
+            self.lm_head = (torch.randn((shape.vocab, h), device=self.device, generator=rep) * 0.02).half() if with_head else None
             # sin/cos tables as model.py:864-877
             inv_freq = 1.0 / (10000.0 ** (torch.arange(0, shape.head_dim, 2, device=self.device).float() / shape.head_dim))
             t = torch.arange(max_seq, device=self.device, dtype=torch.float32)

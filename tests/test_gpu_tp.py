@@ -29,3 +29,18 @@ def test_tp_check_under_torchrun(world):
     tail = p.stdout[-3000:]
     assert p.returncode == 0, tail
     assert f"tp_check world={world}" in p.stdout and "-> OK" in p.stdout, tail
+
+
+@pytest.mark.parametrize("world", [2])
+def test_tp_fused_decode_step_under_torchrun(world):
+    """csrc/decode_step.cu with tp_world > 1 (peer-memory reductions + cross-GPU barrier inside the kernel) against the per-op
+    tensor-parallel path on the same sharded stack (tools/tp_step_check.py)."""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ); env.pop("OMP_NUM_THREADS", None)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29700 + world), os.path.join(ROOT, "tools", "tp_step_check.py"), "--layers", "3"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env, cwd=ROOT)
+    tail = p.stdout[-3000:]
+    assert p.returncode == 0, tail
+    assert f"tp_step_check world={world} -> OK" in p.stdout, tail

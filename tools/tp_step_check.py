@@ -69,6 +69,14 @@ x = xs[0]
 ms_fused = timed(lambda: st.decode_step_fused(x, args.ctx), args.reps)
 h = x.clone()
 ms_perop = timed(lambda: (h.copy_(x), st.decode_step(h, args.ctx)), max(4, args.reps // 4))
+if rank == 0 and os.environ.get("EXL_DS_TRACE"):
+    import numpy as np
+    tr = st.dplan.trace().astype(np.int64)
+    L = min(2, len(st.layers) - 1)
+    med = lambda a_, b_: round(float(np.median(tr[:, L, b_] - tr[:, L, a_])) / 1e3, 2)
+    print(json.dumps({"layer_us": med(0, 14), "QKV": med(0, 2), "B1": med(2, 3), "ATT": med(3, 4), "B2": med(4, 5), "O": med(5, 7),
+                      "B3_local": med(7, 16), "B3_push": med(16, 17), "B3_cross": med(17, 8), "GU": med(8, 10), "B4": med(10, 11), "DOWN": med(11, 13),
+                      "B5_local": med(13, 18), "B5_push": med(18, 19), "B5_cross": med(19, 14)}), flush=True)
 if rank == 0:
     print(json.dumps({"world": world, "model": args.model, "layers": len(st.layers), "ctx": args.ctx, "fused_tp_ms": round(ms_fused, 4),
                       "per_op_tp_nccl_eager_ms": round(ms_perop, 4), "parity_ok": ok, "plan": st.dplan.info()}), flush=True)
