@@ -218,14 +218,16 @@ __device__ __forceinline__ float row_absmax(const uint4& hv)
 
 // contiguous share of n items for CTA c of G
 __device__ __forceinline__ int share_lo(long long n, int c, int G) { return (int)(n * c / G); }
+// share of CTA c in a phase that p_G <= G CTAs take part in: [lo, hi), empty for c >= p_G
+__device__ __forceinline__ int range_lo(long long n, int c, int pG) { return c >= pG ? (int)n : (int)(n * c / pG); }
 // the CTA whose share contains item u (inverse of share_lo)
 __device__ __forceinline__ int cta_of(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
 
-struct Phase { int kind, U, spt, tpm, nmat, mat0, N; float* acc; };     // tpm: tiles per matrix (ATT: units per head)
+struct Phase { int kind, U, spt, tpm, nmat, mat0, N, G; float* acc; };     // G: CTAs that take part in the phase     // tpm: tiles per matrix (ATT: units per head)
 
-__device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
+__device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind, int grid)
 {
-    Phase p; p.kind = kind; p.acc = nullptr; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
+    Phase p; p.kind = kind; p.acc = nullptr; p.G = grid; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
     if (kind == PH_QKV)       { p.spt = a.H / TILE;  p.N = a.HQ; p.nmat = 3; p.mat0 = 0; p.acc = a.acc_qkv; }
     else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; }
     else if (kind == PH_GU)   { p.spt = a.H / TILE;  p.N = a.I;  p.nmat = 2; p.mat0 = 4; p.acc = a.acc_gu; }
@@ -234,6 +236,9 @@ __device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind)
         const int nch = (a.past_len + 15) >> 4;
         p.tpm = nch > 0 ? nch : 1;                          // units per head (one empty unit when there is no history)
         p.U = a.heads * p.tpm;
+        // at most ~7 CTAs per head: the O prologue combines one partial per CTA and head (two rounds of 4 loads); with few heads
+        // per GPU (tensor parallel) the rest of the grid sits this phase out -- its bytes are small then
+        if (a.heads * 7 < grid) p.G = a.heads * 7;
     } else if (kind == PH_HEAD) {
         p.U = a.lm_head ? (int)(((long long)a.vocab * a.H * 2 + W_BYTES - 1) / W_BYTES) : 0;
     } else {
@@ -313,8 +318,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const LayerDesc* L = a.layers + l;
             #pragma unroll 1
             for (int ph = PH_QKV; ph <= PH_DOWN; ph++) {
-                const Phase p = phase_of(a, ph);
-                const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+                const Phase p = phase_of(a, ph, G);
+                const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
                 const int i0 = ((pq - jbase) & 3);
                 jbase += u1 - u0;
                 if (ph == PH_ATT) {
@@ -352,8 +357,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
         }
         {
-            const Phase p = phase_of(a, PH_HEAD);
-            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const Phase p = phase_of(a, PH_HEAD, G);
+            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             const int i0 = ((pq - jbase) & 3);
             const long long total = (long long)a.vocab * a.H * 2;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.lm_head);
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     // with cp.async BEFORE the grid barrier (no registers held), so the phase prologue is left with one L2 round trip (the
     // accumulator) instead of two.  Slot r of wnorm holds the weights of row r of the staging order.
     auto preload_norm = [&](const half* nw, const Phase& p) {
-        const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+        const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
         const int n = min(u1 - u0, p.spt), s0 = u1 > u0 ? u0 % p.spt : 0;
         for (int r = tid; r < n * 16; r += DS_CONSUMERS) {
             int s = s0 + (r >> 4); if (s >= p.spt) s -= p.spt;
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    preload_norm(a.layers[0].ln1, phase_of(a, PH_QKV));
+    preload_norm(a.layers[0].ln1, phase_of(a, PH_QKV, G));
     grid_barrier(a.bar, target, (unsigned)G, tid);
     if (a.tp_world > 1 && cta == 0 && tid == 0) *a.launch_ctr = (unsigned)s_base_x + 1u;      // every CTA has read it (it is past the barrier)
 
@@ -636,8 +641,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const LayerDesc* L = a.layers + l;
         // ======================================================== QKV ========================================================
         {
-            const Phase p = phase_of(a, PH_QKV);
-            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const Phase p = phase_of(a, PH_QKV, G);
+            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             stamp(l, 0);
             if (l > 0) zero_share(a.acc_gu, 2 * a.I);
             rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
@@ -654,8 +659,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 
         // ======================================================== ATT ========================================================
         {
-            const Phase p = phase_of(a, PH_ATT);
-            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const Phase p = phase_of(a, PH_ATT, G);
+            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             if (l > 0) zero_share(a.acc_d, a.H);
             const int nph = p.tpm;
             const float scale = rsqrtf((float)TILE);
@@ -789,7 +794,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     Lt = fmaf(pp[w * PART_LD + 129], wgt, Lt);
                     ov = fmaf(pp[w * PART_LD + d], wgt, ov);
                 }
-                const int slot_id = cta - cta_of((long long)h * nph, p.U, G);
+                const int slot_id = cta - cta_of((long long)h * nph, p.U, p.G);
                 float* dst = a.att_part + ((size_t)h * a.att_slots + slot_id) * PART_LD;
                 dst[d] = ov;
                 if (d == 0) { dst[128] = M; dst[129] = Lt; }
@@ -802,16 +807,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 
         // ========================================================= O =========================================================
         {
-            const Phase p = phase_of(a, PH_O);
-            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const Phase p = phase_of(a, PH_O, G);
+            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             zero_share(a.acc_qkv, 3 * a.HQ);
             if (u1 > u0) {
-                const Phase pa = phase_of(a, PH_ATT);
+                const Phase pa = phase_of(a, PH_ATT, G);
                 stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
                     // softmax-combine of the CTA partials of head k8 / 16 (model.py:402-409), 8 dims per thread, fp16 result.
                     // All loads of up to 8 partials are issued together: one L2 round trip.
                     const int h = k8 >> 4, d0 = (k8 & 15) * 8;
-                    const int c_lo = cta_of((long long)h * pa.tpm, pa.U, G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, G);
+                    const int c_lo = cta_of((long long)h * pa.tpm, pa.U, pa.G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, pa.G);
                     const int ns = c_hi - c_lo + 1;
                     const float* src = a.att_part + (size_t)h * a.att_slots * PART_LD;
                     float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY;
@@ -851,7 +856,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             stamp(l, 6);
             gemv(p, u0, u1);
             jbase += u1 - u0;
-            preload_norm(L->ln2, phase_of(a, PH_GU));
+            preload_norm(L->ln2, phase_of(a, PH_GU, G));
             stamp(l, 7);
         }
         if (a.tp_world > 1) push_partial(a.acc_o, a.push_o, epoch0 + 2u * l, l, 16);
@@ -860,8 +865,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 
         // ========================================================= GU ========================================================
         {
-            const Phase p = phase_of(a, PH_GU);
-            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const Phase p = phase_of(a, PH_GU, G);
+            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             rm = residual_and_norm(a.acc_o, a.tp_world > 1 ? a.slots_o : nullptr, epoch0 + 2u * l);
             if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
             consumer_sync();
@@ -875,8 +880,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 
         // ======================================================== DOWN =======================================================
         {
-            const Phase p = phase_of(a, PH_DOWN);
-            const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+            const Phase p = phase_of(a, PH_DOWN, G);
+            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             zero_share(a.acc_o, a.H);
             if (u1 > u0) {
                 stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
@@ -895,7 +900,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             stamp(l, 12);
             gemv(p, u0, u1);
             jbase += u1 - u0;
-            if (l + 1 < a.n_layers) preload_norm(a.layers[l + 1].ln1, phase_of(a, PH_QKV));
+            if (l + 1 < a.n_layers) preload_norm(a.layers[l + 1].ln1, phase_of(a, PH_QKV, G));
             stamp(l, 13);
         }
         if (a.tp_world > 1) push_partial(a.acc_d, a.push_d, epoch0 + 2u * l + 1u, l, 18);
@@ -908,8 +913,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     if (a.x_out && cta == 0)
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
     if (a.lm_head) {
-        const Phase p = phase_of(a, PH_HEAD);
-        const int u0 = share_lo(p.U, cta, G), u1 = share_lo(p.U, cta + 1, G);
+        const Phase p = phase_of(a, PH_HEAD, G);
+        const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
         {
             const half2 rm2 = __float2half2_rn(rm);
             for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
@@ -1055,7 +1060,7 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     if (e != cudaSuccess || per_sm < 1) return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: kernel does not fit an SM (smem %zu)", p->smem));
     p->grid = ds->num_sms;
     if (const char* eg = getenv("EXL_DS_GRID")) { int v = atoi(eg); if (v >= 1 && v <= ds->num_sms) p->grid = v; }
-    a.att_slots = p->grid / (d->num_heads > 0 ? d->num_heads : 1) + 2;
+    a.att_slots = (p->grid < 7 * d->num_heads ? p->grid / d->num_heads : 7) + 2;
     // scratch: accumulators | attention partials | barrier
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };

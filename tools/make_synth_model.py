@@ -73,8 +73,12 @@ def main():
     def q4(key, K, N):
         G = K // gs
         t[key + ".qweight"] = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev, generator=gen).cpu()
-        t[key + ".qzeros"] = torch.randint(-2**31, 2**31 - 1, (G, N // 8), dtype=torch.int32, device=dev, generator=gen).cpu()
-        t[key + ".scales"] = (torch.rand((G, N), device=dev, generator=gen) * 1.8e-3 + 2e-4).half().cpu()
+        # zero points clustered mid-range (stored nibble 6..9) and gain-normalised scales: see exllama_b200/stack.py synth_q4_device
+        zn = torch.randint(6, 10, (G, N // 8, 8), dtype=torch.int64, device=dev, generator=gen)
+        qz = (zn << (torch.arange(8, device=dev, dtype=torch.int64) * 4)).sum(-1)
+        t[key + ".qzeros"] = torch.where(qz >= 2**31, qz - 2**32, qz).to(torch.int32).cpu()
+        hi = 2.3e-3 * (4096.0 / K) ** 0.5
+        t[key + ".scales"] = (torch.rand((G, N), device=dev, generator=gen) * 0.9 * hi + 0.1 * hi).half().cpu()
         if args.act_order:
             perm = torch.randperm(K, device=dev, generator=gen)
             g_idx = torch.empty(K, dtype=torch.int32, device=dev)
