@@ -26,17 +26,18 @@ from .shapes import SHAPES, LlamaShape  # noqa: E402,F401  (re-exported)
 
 
 def synth_q4_device(K, N, groupsize, device, gen, act_order=False, scale_lo=None, scale_hi=None):
-    """Random GPTQ tensor set on the device, shaped like a real checkpoint: uniform 4-bit weights, zero points clustered around
-    the middle of the range (stored nibble 6..9, i.e. z + 1 = 7..10, as GPTQ produces for roughly symmetric weight groups -- uniform
-    0..15 zeros would give every group a large DC offset and a deep synthetic stack then overflows fp16), and scales sized for a
-    per-layer gain a little below one whatever K is (std(q - z) ~ 4.7, so gain = 4.7 * mean(scale) * sqrt(K) ~ 0.6)."""
+    """Random GPTQ tensor set on the device, shaped like a real checkpoint: uniform 4-bit weights, zero points in the middle of
+    the range (stored nibble 6 or 7, i.e. z + 1 = 7 or 8, mean 7.5 = the mean nibble: zero-mean weights, as GPTQ produces for
+    symmetric weight groups.  A mean offset of even one quantisation step gives every matrix a DC gain of ~scale * K >> 1 and a
+    deep synthetic stack then blows up through its DC mode -- measured: 33B overflowed fp16 within a few layers), and scales sized
+    for a per-layer gain below one whatever K is (std(q - z) ~ 4.6, so gain = 4.6 * mean(scale) * sqrt(K) ~ 0.4)."""
     G = K // groupsize
     if scale_hi is None:
         scale_hi = 2.3e-3 * (4096.0 / K) ** 0.5
     if scale_lo is None:
         scale_lo = 0.1 * scale_hi
     qweight = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=device, generator=gen)
-    zn = torch.randint(6, 10, (G, N // 8, 8), dtype=torch.int64, device=device, generator=gen)
+    zn = torch.randint(6, 8, (G, N // 8, 8), dtype=torch.int64, device=device, generator=gen)
     shifts = (torch.arange(8, device=device, dtype=torch.int64) * 4)
     qz = (zn << shifts).sum(-1)                                   # 8 nibbles per word, nibble n % 8 of word [g, n / 8]
     qzeros = torch.where(qz >= 2**31, qz - 2**32, qz).to(torch.int32)

@@ -73,8 +73,8 @@ def main():
     def q4(key, K, N):
         G = K // gs
         t[key + ".qweight"] = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev, generator=gen).cpu()
-        # zero points clustered mid-range (stored nibble 6..9) and gain-normalised scales: see exllama_b200/stack.py synth_q4_device
-        zn = torch.randint(6, 10, (G, N // 8, 8), dtype=torch.int64, device=dev, generator=gen)
+        # zero points clustered mid-range (stored nibble 6 or 7: zero-mean weights) and gain-normalised scales: see exllama_b200/stack.py synth_q4_device
+        zn = torch.randint(6, 8, (G, N // 8, 8), dtype=torch.int64, device=dev, generator=gen)
         qz = (zn << (torch.arange(8, device=dev, dtype=torch.int64) * 4)).sum(-1)
         t[key + ".qzeros"] = torch.where(qz >= 2**31, qz - 2**32, qz).to(torch.int32).cpu()
         hi = 2.3e-3 * (4096.0 / K) ** 0.5

@@ -32,7 +32,20 @@ for i, L in enumerate(st.layers):
     x2 = x.view(-1, s.hidden)
     if world == 1:
         ext.q4_attn_2(x2, attn.view(-1, hq), L.o.q4, none, none, none); chk(f"L{i} x after o", x2)
+        x_before = x2.clone()
         ext.q4_mlp(x2, L.ln2, s.eps, L.gate.q4, L.up.q4, L.down.q4, none, none, none, none, none, none, none); chk(f"L{i} x after mlp", x2)
+        if os.environ.get("ORACLE"):
+            import numpy as np
+            from oracle import oracle as O
+            def mm(xin, lin, acc=None):
+                xm = None if lin.g_idx is None else O.make_x_map(lin.g_idx.numpy(), lin.qzeros.shape[0])
+                return O.q4_matmul_f64(xin, lin.qweight.cpu().numpy(), lin.qzeros.cpu().numpy(), lin.scales.cpu().numpy(), xm, acc)   # qweight is already sequential
+            xb = x_before.cpu().numpy()
+            xn, _ = O.rms_norm(xb, L.ln2.cpu().numpy(), s.eps)
+            act = O.silu_mul(mm(xn, L.gate).astype(np.float16), mm(xn, L.up).astype(np.float16))
+            want = mm(act, L.down, acc=xb)
+            got = x2.cpu().numpy().astype(np.float64)
+            print(f"L{i} mlp vs oracle: max err {np.abs(got - want).max():.4g}, |want| max {np.abs(want).max():.4g}, rms {np.sqrt((want ** 2).mean()):.4g}", flush=True)
     else:
         oin = st._o_input(attn.view(-1, hq)); chk(f"L{i} o_input", oin)
         tpmod.row_parallel_residual(ext, x2, oin, L.o.q4, rank, None); chk(f"L{i} x after o", x2)
