@@ -27,7 +27,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -57,48 +56,45 @@ def parse():
     return a
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons through NVML during the timed region."""
+class ClockSampler:
+    """SM clock / throttle reasons DURING the timed region, sampled by a separate `nvidia-smi -lms` process (B200_PROFILING.md):
+    an in-process NVML thread was seen to take ~60 ms per sample when several ranks share a box and stalled the launch loop."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
+        self.index, self.proc = index, None
 
-    def run(self):
-        if self.nv is None:
-            return
-        nv = self.nv
-        names = {
-            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-        }
-        while not self.stop_flag:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.02)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def result(self):
-        self.stop_flag = True
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill(); out = ""
+        clocks, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            clocks.append(int(f[0])); mx = int(f[1]) if f[1].isdigit() else mx
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not clocks:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": 0}
+        c = sorted(clocks)
+        return {"sm_mhz": c[len(c) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(c)}
 
 
 def measured_peaks():
@@ -342,7 +338,8 @@ def main():
         graph = None
     else:
         # NCCL inside stream capture hung on this stack; the fused all-reduce kernels are plain launches and capture fine
-        use_graph = not args.no_graph and (world == 1 or fused_ar or os.environ.get("EXL_BENCH_TP_GRAPH", "0") == "1")
+        use_graph = not args.no_graph and (world == 1 or (fused_ar and not args.act_order) or os.environ.get("EXL_BENCH_TP_GRAPH", "0") == "1")
+        # (act-order + tensor parallel falls back to NCCL for the MLP; NCCL inside stream capture hung on this stack in round 1)
         graph = capture(per_op_step) if use_graph else None
         step_device = graph.replay if graph is not None else per_op_step
         launches_per_step = launches_per_op
@@ -351,7 +348,9 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # one GPU's clocks (rank 0's) are reported; the other ranks start nothing beside their launch loop
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.cudart().cudaProfilerStart()          # no-op unless run under `ncu --profile-from-start off`
     e0.record()
@@ -361,7 +360,7 @@ def main():
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.result()
+    clocks = sampler.result() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -484,7 +483,7 @@ def main():
 
     # ------------------------------------------------------------------ tensor parallel: parity + cost of the collective
     tp_info = None
-    if world > 1:
+    if world > 1 and not use_step:
         from exllama_b200 import tp as tpmod
         tp_info = {}
         if fused_ar:
@@ -583,7 +582,12 @@ def main():
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        os._exit(0)            # skip NCCL / IPC teardown: a hang there once cost a 15-minute timeout on 4 GPUs
 
 
 if __name__ == "__main__":
