@@ -2,7 +2,7 @@
 # usage: tools/run_tp.sh N tag [bench args...]   -> gpurun_out/bench_r2_<tag>_tpN.json
 N=$1; tag=$2; shift 2
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N "$@" > gpurun_out/bench_r2_${tag}_tp$N.json 2> gpurun_out/bench_r2_${tag}_tp$N.err
+timeout ${RUN_TIMEOUT:-900} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N "$@" > gpurun_out/bench_r2_${tag}_tp$N.json 2> gpurun_out/bench_r2_${tag}_tp$N.err
 echo "rc=$? $tag tp$N"; python - <<PY
 import json
 try:
