@@ -274,7 +274,7 @@ def main():
         from exllama_b200 import tp as tpmod
         tpmod.init_fused_allreduce(ext, dev.index)      # row-parallel projections: GEMV + peer-memory all-reduce in one kernel
         fused_ar = True
-    use_step = not args.act_order and not args.no_fused_step
+    use_step = not args.no_fused_step and not (args.act_order and world > 1)      # act-order under TP: per-op path (o_proj needs the all-gathered attention output)
     if use_step:
         stack.make_plan()
     torch.cuda.synchronize()

@@ -63,6 +63,7 @@ struct alignas(64) LayerDesc
     CUtensorMap tw[7];                 // q k v o gate up down: exl_q4_matrix::tmap_w3 (one 8 KB unit per op)
     CUtensorMap ts[7];                 // ::tmap_sc
     CUtensorMap tz[7];                 // ::tmap_qz
+    const uint32_t* xmap[7];           // act-order: x column feeding sequential row k of each matrix (exl_q4_matrix::x_map), else NULL
     const half* ln1; const half* ln2;
     half* kc; half* vc;                // [heads, max_seq, 128]
 };
@@ -75,6 +76,10 @@ struct StepArgs
     int gshift;                        // log2(groupsize / 32); 30 = one group per matrix
     int depth;                         // ring stages per pipeline (4 pipelines)
     int spt_max;                       // max K / 128 over the phases
+    int act;                           // act-order matrices present: x is gathered through each matrix's x_map while it is staged; the
+                                       // matrices of a phase then need their own quantised x (two staging slots), and o_proj's input
+                                       // (a gather over all heads) goes through one extra combine step + barrier
+    half* attn_vec;                    // [HQ] combined attention output (act-order only)
     float eps;
     const half* x_in; half* x_out;     // [H] input hidden state; final hidden state (before the final norm), optional
     const half* sin; const half* cos;  // [max_seq, 128]
@@ -93,6 +98,8 @@ struct StepArgs
     uint2* push_o[8]; uint2* push_d[8];          // where THIS rank's partial goes on rank r: slots_o / slots_d of rank r, row tp_rank
     const uint2* slots_o; const uint2* slots_d;  // own receive slots [world][H] of {float bits, epoch}
     unsigned* launch_ctr;                        // launches completed so far (all ranks run the same number)
+    int tp_reduce;                               // world >= 4: each CTA totals ITS share of the ranks' partials after the push and a second local
+                                                 // barrier publishes the complete sum (prologues then read one vector instead of world)
     int debug;                         // EXL_DS_DEBUG bitmask (bring-up experiments): 1 skip GEMV math, 2 skip attention math, 4 skip head math
     unsigned long long* trace;         // optional [G][TRACE_LAYERS][16] globaltimer stamps of CTA thread 0 (EXL_DS_TRACE=1), else NULL
 };
@@ -207,6 +214,17 @@ __device__ __forceinline__ int quantise_row(const uint4& hv, float inv, uint4& o
     }
     return sum;
 }
+// the 8 x columns feeding k8-row k8 of an act-order matrix (identity when the matrix has no x_map)
+__device__ __forceinline__ void load_map8(const uint32_t* map, int k8, uint32_t (&idx)[8])
+{
+    if (map) {
+        const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(map) + 2 * k8), m1 = __ldg(reinterpret_cast<const uint4*>(map) + 2 * k8 + 1);
+        idx[0] = m0.x; idx[1] = m0.y; idx[2] = m0.z; idx[3] = m0.w; idx[4] = m1.x; idx[5] = m1.y; idx[6] = m1.z; idx[7] = m1.w;
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 8; i++) idx[i] = (uint32_t)(k8 * 8 + i);
+    }
+}
 __device__ __forceinline__ float row_absmax(const uint4& hv)
 {
     const half2* h = reinterpret_cast<const half2*>(&hv);
@@ -276,9 +294,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     extern __shared__ __align__(128) unsigned char smem[];
     const int depth = a.depth, nst = 4 * a.depth;
     unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);      // nst x STAGE_STRIDE: pipeline g owns stages [g * depth, (g + 1) * depth)
-    unsigned char* xs = ring + (size_t)nst * STAGE_STRIDE;                            // spt_max x 16 k8-rows x 16 B: quantised x planes by K stage
-    unsigned char* segt = xs + (size_t)a.spt_max * 256;                                // spt_max x 4 x {sum x_q, x scale}
-    half* xres = reinterpret_cast<half*>(segt + (size_t)a.spt_max * 32);              // [H] residual stream (fp16, as the reference keeps it)
+    // staging slot 0: spt_max K stages; act-order adds slot 1 (H / 128 stages: only the multi-matrix phases, whose K is H, need it --
+    // the two matrices a CTA's range can touch have different x_maps)
+    const int xstages = a.spt_max + (a.act ? a.H / TILE : 0);
+    const uint32_t xs_slot = (uint32_t)a.spt_max * 256u, seg_slot = (uint32_t)a.spt_max * 32u;
+    unsigned char* xs = ring + (size_t)nst * STAGE_STRIDE;                            // xstages x 16 k8-rows x 16 B: quantised x planes by K stage
+    unsigned char* segt = xs + (size_t)xstages * 256;                                  // xstages x 4 x {sum x_q, x scale}
+    half* xres = reinterpret_cast<half*>(segt + (size_t)xstages * 32);                // [H] residual stream (fp16, as the reference keeps it)
     float* parts = reinterpret_cast<float*>(xres + a.H);                               // [2 segments][17][PART_LD] attention partials of the warps (+ the new token)
     float* q_s = parts + 2 * 17 * PART_LD;                                             // [2][128] scaled q of the segment's head
     float* kn_s = q_s + 2 * TILE;                                                      // [2][128] newest k row (after rope)
@@ -411,6 +433,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     // with cp.async BEFORE the grid barrier (no registers held), so the phase prologue is left with one L2 round trip (the
     // accumulator) instead of two.  Slot r of wnorm holds the weights of row r of the staging order.
     auto preload_norm = [&](const half* nw, const Phase& p) {
+        if (a.act) return;                                    // act-order: the getter gathers the weights itself
         const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
         const int n = min(u1 - u0, p.spt), s0 = u1 > u0 ? u0 % p.spt : 0;
         for (int r = tid; r < n * 16; r += DS_CONSUMERS) {
@@ -482,7 +505,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
 
     // ---- quantise the K stages [s0, s0 + n) (cyclic mod spt) of the phase input into xs / segt; `get(k8, it)` yields 8 fp16 values ----
-    auto stage_x = [&](int s0, int n, int spt, auto get) {
+    auto stage_x = [&](int s0, int n, int spt, auto get, int slot = 0) {
+        unsigned char* xs_w = xs + (size_t)slot * xs_slot; unsigned char* seg_w = segt + (size_t)slot * seg_slot;
         const int nrows = n * 16;
         int it = 0;
         for (int base = 0; base < nrows; base += DS_CONSUMERS, it++) {
@@ -497,9 +521,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             int sum = quantise_row(hv, mx > 0.f ? 32639.0f / mx : 0.f, q);
             for (int o = rpg >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             if (act) {
-                *reinterpret_cast<uint4*>(xs + (size_t)s * 256 + rr * 16) = q;
+                *reinterpret_cast<uint4*>(xs_w + (size_t)s * 256 + rr * 16) = q;
                 if ((rr & (rpg - 1)) == 0)
-                    *reinterpret_cast<float2*>(segt + (size_t)s * 32 + (rr / rpg) * 8) = make_float2(__int_as_float(sum), mx * (1.0f / 32639.0f));
+                    *reinterpret_cast<float2*>(seg_w + (size_t)s * 32 + (rr / rpg) * 8) = make_float2(__int_as_float(sum), mx * (1.0f / 32639.0f));
             }
         }
     };
@@ -512,6 +536,35 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             #pragma unroll
             for (int i = 0; i < 4; i++) h[i] = __hmul2(__hmul2(h[i], rm2), w2[i]);      // rms_norm.cu:118-131
             return xv;
+        };
+    };
+
+    // ---- stage the phase input for every matrix the CTA's unit range touches.  Without act-order all matrices of a phase share x
+    // (one staging); with act-order each matrix gathers x through its own x_map (q4_matmul.cu:239-299 / column_remap.cu:27-34), so a
+    // range that crosses a matrix boundary stages twice, into slot (matrix - first matrix).  make_get(m) returns the 8-value getter.
+    auto stage_phase = [&](const Phase& p, int u0, int u1, auto make_get) {
+        if (u1 <= u0) return;
+        const int per_mat = p.tpm * p.spt;
+        const int mi0 = u0 / per_mat, mi1 = a.act ? (u1 - 1) / per_mat : mi0;
+        for (int mi = mi0; mi <= mi1; mi++) {
+            const int ua = a.act ? max(u0, mi * per_mat) : u0, ub = a.act ? min(u1, (mi + 1) * per_mat) : u1;
+            stage_x(ua % p.spt, min(ub - ua, p.spt), p.spt, make_get(p.mat0 + mi), mi - mi0);
+        }
+    };
+    // x (residual stream in shared memory) -> (x * rm) * w, gathered through an x_map when there is one (rms_norm.cu:118-131)
+    auto norm_get_map = [&](const half* nw, float rmf, const uint32_t* map) {
+        return [=](int k8, int) -> uint4 {
+            uint32_t idx[8];
+            load_map8(map, k8, idx);
+            const half2 rm2 = __float2half2_rn(rmf);
+            uint4 r; half2* h = reinterpret_cast<half2*>(&r);
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const half2 xv = __halves2half2(xres[idx[2 * i]], xres[idx[2 * i + 1]]);
+                const half2 wv = __halves2half2(__ldg(nw + idx[2 * i]), __ldg(nw + idx[2 * i + 1]));
+                h[i] = __hmul2(__hmul2(xv, rm2), wv);
+            }
+            return r;
         };
     };
 
@@ -541,9 +594,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const uint32_t sc_lane = (uint32_t)(META_SC + lane_col * 2), zq_lane = (uint32_t)(META_ZQ + (lane_col >> 3) * 4);
         const uint32_t zshift = (uint32_t)((lane_col & 4) * 4);
         const uint32_t seg_a = smem_u32(segt);
+        const int mi_first = a.act ? (u0 / p.spt) / p.tpm : 0;       // staging slot of a tile = its matrix - the first matrix of the CTA's range
+        uint32_t xoff = a.act ? (uint32_t)(cur_tile / p.tpm - mi_first) * xs_slot : 0u, soff = a.act ? (uint32_t)(cur_tile / p.tpm - mi_first) * seg_slot : 0u;
         bool ready = mbar_try(full0 + ls * 8, par);
         for (; u < u1; u += 4) {
-            if (tile != cur_tile) { flush_tile(); cur_tile = tile; }
+            if (tile != cur_tile) {
+                flush_tile(); cur_tile = tile;
+                if (a.act) { const uint32_t sl = (uint32_t)(tile / p.tpm - mi_first); xoff = sl * xs_slot; soff = sl * seg_slot; }
+            }
             const uint32_t tok = mbar_wait_tok(full0 + ls * 8, par, ready);
             const int ls_cur = ls;
             if (++ls == depth) { ls = 0; par ^= 1u; }
@@ -552,7 +610,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             float dep = 0.f;
             if (!(a.debug & 1)) {
                 const uint32_t sb = ring_a + (uint32_t)ls_cur * STAGE_STRIDE + tok;
-                const uint32_t xr = x_lane + (uint32_t)s * xstage + tok;
+                const uint32_t xr = x_lane + (uint32_t)s * xstage + xoff + tok;
                 uint4 w[4]; uint2 xv[4];
                 w[0] = lds128(sb + w_lane);         w[1] = lds128(sb + w_lane4);
                 w[2] = lds128(sb + w_lane + 1024);  w[3] = lds128(sb + w_lane4 + 1024);
@@ -566,7 +624,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     const int row = UPSEG == 4 ? 0 : e;
                     sc2[e] = lds64(sb + sc_lane + row * 256);
                     zw[e] = lds32(sb + zq_lane + row * 64);
-                    sg[e] = lds64(seg_a + (uint32_t)s * 32u + e * 8 + tok);
+                    sg[e] = lds64(seg_a + (uint32_t)s * 32u + e * 8 + soff + tok);
                 }
                 // two independent accumulator sets (even / odd units) halve the dependent IMMA chain
                 int ia[2][8];
@@ -633,6 +691,32 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(reinterpret_cast<uint4*>(push[r]) + lo + j), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
         }
         stamp(l, ev + 1);
+        if (a.tp_reduce) {
+            // total this CTA's share over the ranks in rank order (peers' pairs polled until the epoch shows up), write it back into the
+            // accumulator, and publish with a second local barrier: the prologue that follows reads ONE complete vector
+            const uint4* rx = reinterpret_cast<const uint4*>(push == a.push_o ? a.slots_o : a.slots_d);
+            for (int j = tid; j < n2; j += DS_CONSUMERS) {
+                const float2 own = __ldcg(reinterpret_cast<const float2*>(acc) + lo + j);
+                float2 tot = make_float2(0.f, 0.f);
+                for (int r = 0; r < a.tp_world; r++) {
+                    float2 e = own;
+                    if (r != a.tp_rank) {
+                        const uint4* sp = rx + (size_t)r * (a.H >> 1) + lo + j;
+                        uint4 v;
+                        const unsigned long long t0 = gtime();
+                        unsigned spin = 0;
+                        do {
+                            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(sp) : "memory");
+                            if ((++spin & 1023u) == 0 && gtime() - t0 > WAIT_NS) __trap();
+                        } while (v.y != epoch || v.w != epoch);
+                        e = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
+                    }
+                    tot.x += e.x; tot.y += e.y;
+                }
+                reinterpret_cast<float2*>(const_cast<float*>(acc))[lo + j] = tot;
+            }
+            grid_barrier(a.bar, target, (unsigned)G, tid);
+        }
     };
 
     float rm = 0.f;
@@ -645,9 +729,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             stamp(l, 0);
             if (l > 0) zero_share(a.acc_gu, 2 * a.I);
-            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
+            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && !a.tp_reduce && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
             stamp(l, 15);
-            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
+            if (!a.act) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
+            else stage_phase(p, u0, u1, [&](int m) { return norm_get_map(L->ln1, rm, L->xmap[m]); });
             consumer_sync();
             stamp(l, 1);
             gemv(p, u0, u1);
@@ -810,46 +895,64 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const Phase p = phase_of(a, PH_O, G);
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             zero_share(a.acc_qkv, 3 * a.HQ);
-            if (u1 > u0) {
-                const Phase pa = phase_of(a, PH_ATT, G);
-                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
-                    // softmax-combine of the CTA partials of head k8 / 16 (model.py:402-409), 8 dims per thread, fp16 result.
-                    // All loads of up to 8 partials are issued together: one L2 round trip.
-                    const int h = k8 >> 4, d0 = (k8 & 15) * 8;
-                    const int c_lo = cta_of((long long)h * pa.tpm, pa.U, pa.G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, pa.G);
-                    const int ns = c_hi - c_lo + 1;
-                    const float* src = a.att_part + (size_t)h * a.att_slots * PART_LD;
-                    float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY;
-                    for (int b = 0; b < ns; b += 4) {
-                        float mw[4], lw[4]; float4 o0[4], o1[4];
-                        #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const bool ok = b + q < ns;
-                            const float* sp = src + (size_t)(ok ? b + q : 0) * PART_LD;
-                            mw[q] = ok ? __ldcg(sp + 128) : -INFINITY; lw[q] = __ldcg(sp + 129);
-                            o0[q] = ldcg4(sp + d0); o1[q] = ldcg4(sp + d0 + 4);
-                        }
-                        float Mn = M;
-                        #pragma unroll
-                        for (int q = 0; q < 4; q++) Mn = fmaxf(Mn, mw[q]);
-                        const float resc = M == -INFINITY ? 0.f : __expf(M - Mn);
-                        Lt *= resc;
-                        #pragma unroll
-                        for (int i = 0; i < 8; i++) ov[i] *= resc;
-                        M = Mn;
-                        #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const float wgt = mw[q] == -INFINITY ? 0.f : __expf(mw[q] - M);
-                            Lt = fmaf(lw[q], wgt, Lt);
-                            ov[0] = fmaf(o0[q].x, wgt, ov[0]); ov[1] = fmaf(o0[q].y, wgt, ov[1]); ov[2] = fmaf(o0[q].z, wgt, ov[2]); ov[3] = fmaf(o0[q].w, wgt, ov[3]);
-                            ov[4] = fmaf(o1[q].x, wgt, ov[4]); ov[5] = fmaf(o1[q].y, wgt, ov[5]); ov[6] = fmaf(o1[q].z, wgt, ov[6]); ov[7] = fmaf(o1[q].w, wgt, ov[7]);
-                        }
-                    }
-                    const float inv = 1.0f / Lt;
-                    uint4 r; half2* hh = reinterpret_cast<half2*>(&r);
+            const Phase pa = phase_of(a, PH_ATT, G);
+            // softmax-combine of the CTA partials of one head (model.py:402-409), 8 dims per thread, fp16 result.
+            // All loads of up to 4 partials per round are issued together: one L2 round trip per round.
+            auto combine8 = [&](int h, int d0) -> uint4 {
+                const int c_lo = cta_of((long long)h * pa.tpm, pa.U, pa.G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, pa.G);
+                const int ns = c_hi - c_lo + 1;
+                const float* src = a.att_part + (size_t)h * a.att_slots * PART_LD;
+                float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY;
+                for (int b = 0; b < ns; b += 4) {
+                    float mw[4], lw[4]; float4 o0[4], o1[4];
                     #pragma unroll
-                    for (int i = 0; i < 4; i++) hh[i] = __floats2half2_rn(ov[2 * i] * inv, ov[2 * i + 1] * inv);
-                    return r;
+                    for (int q = 0; q < 4; q++) {
+                        const bool ok = b + q < ns;
+                        const float* sp = src + (size_t)(ok ? b + q : 0) * PART_LD;
+                        mw[q] = ok ? __ldcg(sp + 128) : -INFINITY; lw[q] = __ldcg(sp + 129);
+                        o0[q] = ldcg4(sp + d0); o1[q] = ldcg4(sp + d0 + 4);
+                    }
+                    float Mn = M;
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) Mn = fmaxf(Mn, mw[q]);
+                    const float resc = M == -INFINITY ? 0.f : __expf(M - Mn);
+                    Lt *= resc;
+                    #pragma unroll
+                    for (int i = 0; i < 8; i++) ov[i] *= resc;
+                    M = Mn;
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float wgt = mw[q] == -INFINITY ? 0.f : __expf(mw[q] - M);
+                        Lt = fmaf(lw[q], wgt, Lt);
+                        ov[0] = fmaf(o0[q].x, wgt, ov[0]); ov[1] = fmaf(o0[q].y, wgt, ov[1]); ov[2] = fmaf(o0[q].z, wgt, ov[2]); ov[3] = fmaf(o0[q].w, wgt, ov[3]);
+                        ov[4] = fmaf(o1[q].x, wgt, ov[4]); ov[5] = fmaf(o1[q].y, wgt, ov[5]); ov[6] = fmaf(o1[q].z, wgt, ov[6]); ov[7] = fmaf(o1[q].w, wgt, ov[7]);
+                    }
+                }
+                const float inv = 1.0f / Lt;
+                uint4 r; half2* hh = reinterpret_cast<half2*>(&r);
+                #pragma unroll
+                for (int i = 0; i < 4; i++) hh[i] = __floats2half2_rn(ov[2 * i] * inv, ov[2 * i + 1] * inv);
+                return r;
+            };
+            if (!a.act) {
+                // stage k of o_proj is head k: the CTA combines exactly the heads its K range needs
+                if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 { return combine8(k8 >> 4, (k8 & 15) * 8); });
+            } else {
+                // act-order o_proj: its input is a gather over ALL heads (x_map), so the combined attention output is first written
+                // to L2 once (head h by CTA h mod grid), one extra grid barrier, then every CTA gathers what its K range needs
+                for (int h = cta; h < a.heads; h += G)
+                    if (tid < 16) reinterpret_cast<uint4*>(a.attn_vec + (size_t)h * TILE)[tid] = combine8(h, tid * 8);
+                grid_barrier(a.bar, target, (unsigned)G, tid);
+                const uint32_t* map = L->xmap[3];
+                stage_phase(p, u0, u1, [&](int) {
+                    return [=](int k8, int) -> uint4 {
+                        uint32_t idx[8];
+                        load_map8(map, k8, idx);
+                        uint4 r; half* hh = reinterpret_cast<half*>(&r);
+                        #pragma unroll
+                        for (int i = 0; i < 8; i++) hh[i] = __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(a.attn_vec) + idx[i]));
+                        return r;
+                    };
                 });
             }
             consumer_sync();
@@ -867,8 +970,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_GU, G);
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
-            rm = residual_and_norm(a.acc_o, a.tp_world > 1 ? a.slots_o : nullptr, epoch0 + 2u * l);
-            if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm));
+            rm = residual_and_norm(a.acc_o, (a.tp_world > 1 && !a.tp_reduce) ? a.slots_o : nullptr, epoch0 + 2u * l);
+            if (!a.act) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
+            else stage_phase(p, u0, u1, [&](int m) { return norm_get_map(L->ln2, rm, L->xmap[m]); });
             consumer_sync();
             stamp(l, 9);
             gemv(p, u0, u1);
@@ -883,8 +987,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const Phase p = phase_of(a, PH_DOWN, G);
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             zero_share(a.acc_o, a.H);
-            if (u1 > u0) {
-                stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
+            if (!a.act) {
+                if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
                     // silu(gate) * up on the fp16-rounded projections (q4_mlp.cu:27-36,46-88)
                     const float4 g0 = ldcg4(a.acc_gu + k8 * 8), g1 = ldcg4(a.acc_gu + k8 * 8 + 4);
                     const float4 u0v = ldcg4(a.acc_gu + a.I + k8 * 8), u1v = ldcg4(a.acc_gu + a.I + k8 * 8 + 4);
@@ -894,6 +998,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     #pragma unroll
                     for (int i = 0; i < 8; i++) hh[i] = __hmul(silu_h(__float2half_rn(gf[i])), __float2half_rn(uf[i]));
                     return r;
+                });
+            } else {
+                const uint32_t* map = L->xmap[6];
+                stage_phase(p, u0, u1, [&](int) {
+                    return [=](int k8, int) -> uint4 {
+                        uint32_t idx[8];
+                        load_map8(map, k8, idx);
+                        uint4 r; half* hh = reinterpret_cast<half*>(&r);
+                        #pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            hh[i] = __hmul(silu_h(__float2half_rn(__ldcg(a.acc_gu + idx[i]))), __float2half_rn(__ldcg(a.acc_gu + a.I + idx[i])));
+                        return r;
+                    };
                 });
             }
             consumer_sync();
@@ -909,7 +1026,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     }
 
     // ========================================================= HEAD ==========================================================
-    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && a.n_layers > 0) ? a.slots_d : nullptr, epoch0 + 2u * (a.n_layers - 1) + 1u);
+    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && !a.tp_reduce && a.n_layers > 0) ? a.slots_d : nullptr, epoch0 + 2u * (a.n_layers - 1) + 1u);
     if (a.x_out && cta == 0)
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
     if (a.lm_head) {
@@ -1015,19 +1132,20 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
         while ((1 << sh) < gs32) sh++;
     } else sh = 30;
     std::vector<LayerDesc> L((size_t)d->n_layers);
+    bool any_act = false;
     const int expectK[7] = {H, H, H, HQ, H, H, I}, expectN[7] = {HQ, HQ, HQ, H, I, I, H};
     for (int l = 0; l < d->n_layers; l++) {
         memset(&L[l], 0, sizeof(LayerDesc));
         for (int i = 0; i < 7; i++) {
             const exl_q4_matrix* w = d->mats[l * 7 + i];
             if (!w) return exl_set_err(EXL_ERR_STATE, "decode_plan: NULL handle (layer %d matrix %d)", l, i);
-            if (w->x_map) return exl_set_err(EXL_ERR_ARG, "decode_plan: act-order matrices are not supported by the fused step (use the per-op path)");
+            if (w->x_map) any_act = true;
             if (w->K != expectK[i] || w->N != expectN[i] || w->device != q0->device)
                 return exl_set_err(EXL_ERR_ARG, "decode_plan: layer %d matrix %d is %d x %d, expected %d x %d", l, i, w->K, w->N, expectK[i], expectN[i]);
             const bool one = q0->groups == 1;
             if ((one && w->groups != 1) || (!one && w->groupsize != gs)) return exl_set_err(EXL_ERR_ARG, "decode_plan: mixed group sizes");
             if (!w->valid3) return exl_set_err(EXL_ERR_ARG, "decode_plan: layer %d matrix %d has no unit tensor maps (width %% 128 != 0)", l, i);
-            L[l].tw[i] = w->tmap_w3; L[l].ts[i] = w->tmap_sc; L[l].tz[i] = w->tmap_qz;
+            L[l].tw[i] = w->tmap_w3; L[l].ts[i] = w->tmap_sc; L[l].tz[i] = w->tmap_qz; L[l].xmap[i] = w->x_map;
         }
         L[l].ln1 = (const half*)d->ln1[l]; L[l].ln2 = (const half*)d->ln2[l];
         L[l].kc = (half*)d->key_cache[l]; L[l].vc = (half*)d->value_cache[l];
@@ -1041,9 +1159,12 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     a.final_norm = (const half*)d->final_norm; a.lm_head = (const half*)d->lm_head; a.vocab = d->lm_head ? d->vocab : 0;
     if (d->lm_head && (!d->final_norm || d->vocab % 4)) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: lm_head needs final_norm and vocab %% 4 == 0"));
     a.spt_max = (H > I ? H : I) / TILE; if (HQ / TILE > a.spt_max) a.spt_max = HQ / TILE;
+    a.act = any_act ? 1 : 0;
+    if (any_act && d->tp_world > 1)
+        return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: act-order matrices under tensor parallelism are not supported by the fused step (o_proj needs the all-gathered attention output): use the per-op path"));
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
-    const size_t fixed = 1024 + (size_t)a.spt_max * (256 + 32) + (size_t)H * 2 + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + (size_t)H * 2 /* wnorm */ + 1024 /* static */;
+    const size_t fixed = 1024 + (size_t)(a.spt_max + (any_act ? H / TILE : 0)) * (256 + 32) + (size_t)H * 2 + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + (size_t)H * 2 /* wnorm */ + 1024 /* static */;
     int depth = (int)(((size_t)dev_smem - fixed) / STAGE_STRIDE) / 4;
     if (const char* e = getenv("EXL_DS_DEPTH")) { int v = atoi(e); if (v >= 1 && v < depth) depth = v; }
     if (depth > MAX_DEPTH) depth = MAX_DEPTH;
@@ -1065,7 +1186,7 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_qkv = take((size_t)3 * HQ * 4), o_o = take((size_t)H * 4), o_gu = take((size_t)2 * I * 4), o_d = take((size_t)H * 4);
-    const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256);
+    const size_t o_att = take((size_t)d->num_heads * a.att_slots * PART_LD * 4), o_bar = take(256), o_av = take((size_t)HQ * 2);
     const bool want_trace = getenv("EXL_DS_TRACE") != nullptr;
     const size_t o_trace = want_trace ? take((size_t)p->grid * TRACE_LAYERS * 24 * 8) : 0;
     const int W = d->tp_world > 1 ? d->tp_world : 1;
@@ -1082,8 +1203,11 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     a.acc_o = (float*)(p->d_scratch + o_o); a.acc_d = (float*)(p->d_scratch + o_d);
     a.slots_o = (const uint2*)(p->d_shared + p->shared_o); a.slots_d = (const uint2*)(p->d_shared + p->shared_d);
     a.launch_ctr = (unsigned*)(p->d_scratch + o_bar + 64);
+    a.attn_vec = (half*)(p->d_scratch + o_av);
     a.tp_rank = d->tp_world > 1 ? d->tp_rank : 0; a.tp_world = d->tp_world > 1 ? d->tp_world : 1;
     if (a.tp_world > 8 || a.tp_rank < 0 || a.tp_rank >= a.tp_world) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: bad tensor-parallel rank %d / world %d", d->tp_rank, d->tp_world));
+    a.tp_reduce = a.tp_world >= 4 ? 1 : 0;
+    if (const char* er = getenv("EXL_DS_TP_REDUCE")) a.tp_reduce = (atoi(er) != 0 && a.tp_world > 1) ? 1 : 0;
     p->peer_base[a.tp_rank] = p->d_shared;
     a.push_o[a.tp_rank] = nullptr; a.push_d[a.tp_rank] = nullptr;
     p->peers_ready = a.tp_world == 1;
@@ -1140,7 +1264,7 @@ extern "C" int exl_decode_plan_info(const exl_decode_plan* p, int* grid, int* ri
 {
     if (!p) return exl_set_err(EXL_ERR_STATE, "decode_plan_info: NULL plan");
     if (grid) *grid = p->grid; if (ring_stages) *ring_stages = 4 * p->args.depth; if (smem_bytes) *smem_bytes = (int64_t)p->smem;
-    if (barriers_per_step) *barriers_per_step = 1 + 5 * (int64_t)p->args.n_layers;
+    if (barriers_per_step) *barriers_per_step = 1 + (5 + (p->args.act ? 1 : 0) + (p->args.tp_world > 1 ? (p->args.tp_reduce ? 4 : 2) : 0)) * (int64_t)p->args.n_layers;
     return EXL_OK;
 }
 

@@ -10,11 +10,11 @@ from helpers import assert_close_ref64
 pytestmark = pytest.mark.gpu
 
 
-def _mk_stack(hidden, inter, layers, heads, gs, max_seq, vocab=2048, seed=3):
+def _mk_stack(hidden, inter, layers, heads, gs, max_seq, vocab=2048, seed=3, act=False):
     import torch
     from exllama_b200.stack import DecodeStack, LlamaShape
     shape = LlamaShape("synthetic", hidden, inter, layers, heads, vocab=vocab)
-    st = DecodeStack(shape, groupsize=gs, act_order=False, device="cuda:0", max_seq=max_seq, seed=seed)
+    st = DecodeStack(shape, groupsize=gs, act_order=act, device="cuda:0", max_seq=max_seq, seed=seed)
     g = torch.Generator(device="cuda"); g.manual_seed(seed + 100)
     for kc, vc in zip(st.key_cache, st.value_cache):
         kc.copy_((torch.randn(kc.shape, device="cuda", generator=g) * 0.5).half())
@@ -31,7 +31,9 @@ def _oracle_step(oracle, st, x, past):
     rows = []
 
     def mm(xin, lin, acc=None):
-        return oracle.q4_matmul_f64(xin, lin.qweight.cpu().numpy(), lin.qzeros.cpu().numpy(), lin.scales.cpu().numpy(), None, acc)
+        # make_q4 has already rewritten an act-order qweight into sequential order (q4_matrix.cu:159): contract with the x gather
+        xm = None if lin.g_idx is None else oracle.make_x_map(lin.g_idx.numpy(), lin.qzeros.shape[0])
+        return oracle.q4_matmul_f64(xin, lin.qweight.cpu().numpy(), lin.qzeros.cpu().numpy(), lin.scales.cpu().numpy(), xm, acc)
     for i, L in enumerate(st.layers):
         xn, _ = oracle.rms_norm(x, L.ln1.cpu().numpy(), s.eps)
         q = mm(xn, L.q).astype(np.float16); k = mm(xn, L.k).astype(np.float16); v = mm(xn, L.v).astype(np.float16)
@@ -50,11 +52,11 @@ def _oracle_step(oracle, st, x, past):
     return x, logits, rows
 
 
-@pytest.mark.parametrize("gs", [128, 32, 256])
+@pytest.mark.parametrize("gs,act", [(128, False), (32, False), (256, False), (128, True), (32, True)])
 @pytest.mark.parametrize("past", [0, 1, 16, 37, 200])
-def test_fused_step_vs_oracle_and_per_op_path(oracle, gs, past):
+def test_fused_step_vs_oracle_and_per_op_path(oracle, gs, act, past):
     import torch
-    st = _mk_stack(1024, 2816 if gs != 256 else 2816 - 2816 % 256, 2, 8, gs, 256)
+    st = _mk_stack(1024, 2816, 2, 8, gs, 256, act=act)
     st.make_plan()
     info = st.dplan.info()
     assert info["grid"] >= 100 and info["ring_stages"] >= 8, info
@@ -137,11 +139,18 @@ def test_fused_step_7b_shape_long_context(oracle):
     st.dplan.close(); st.close()
 
 
-def test_fused_step_rejects_act_order():
+def test_fused_step_act_order_13b_shape(oracle):
+    """BASELINE config 3 shape (hidden 5120, inter 13824, 40 heads, act-order), 2 layers at ctx 1920: against the per-op path."""
     import torch
-    from exllama_b200 import capi
-    from exllama_b200.stack import DecodeStack, LlamaShape
-    st = DecodeStack(LlamaShape("synthetic", 1024, 2816, 1, 8, vocab=512), groupsize=128, act_order=True, device="cuda:0", max_seq=64)
-    with pytest.raises(capi.ExlError, match="act-order"):
-        st.make_plan()
-    st.close()
+    st = _mk_stack(5120, 13824, 2, 40, 128, 2048, vocab=32000, seed=13, act=True)
+    st.make_plan()
+    x = (torch.randn((1, 1, 5120), device="cuda") * 0.5).half()
+    snap = [(kc.clone(), vc.clone()) for kc, vc in zip(st.key_cache, st.value_cache)]
+    ref = st.decode_step(x.clone(), 1920).clone()
+    for (kc, vc), (k0, v0) in zip(zip(st.key_cache, st.value_cache), snap):
+        kc.copy_(k0); vc.copy_(v0)
+    got = st.decode_step_fused(x, 1920)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert_close_ref64(got.cpu().numpy().reshape(-1), ref.cpu().numpy().reshape(-1).astype(np.float64), rel=1.5e-2, rms=1.5e-2, what="13B-shape act-order logits")
+    st.dplan.close(); st.close()
