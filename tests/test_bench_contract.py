@@ -15,21 +15,23 @@ def _line(name):
         return json.loads([l for l in f if l.startswith("{")][-1])
 
 
-@pytest.mark.parametrize("name", ["bench_r1.json", "bench_r1_tp2.json", "bench_r1_tp4.json"])
+@pytest.mark.parametrize("name", ["bench_r1.json", "bench_r1_tp2.json", "bench_r1_tp4.json", "bench_r2.json", "bench_r2_7b_tp2.json", "bench_r2_65b_seq4096_tp8.json"])
 def test_bench_line_keys(name):
+    if not os.path.exists(os.path.join(ROOT, "profiles", name)):
+        pytest.skip(name + " not committed yet")
     d = _line(name)
     for k in BASE + ["gpu_launches", "clocks", "roofline"]:
         assert k in d, k
     assert "workload" in d["config"] and "model" not in d["config"]
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
-    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["clocks"] is None or set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     r = d["roofline"]
     assert set(r) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and r["bound"] in ("hbm", "tensor")
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["frac"] is None or abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
     assert d["gpu_launches"] > 0 and d["warmup"] >= 3 and d["higher_is_better"] is True
     if d["n_gpus"] == 1:
         c = d["cpu_baseline"]
-        assert set(c) >= {"value", "unit", "cores", "kind", "sample"} and c["kind"] in ("reference", "port")
+        assert c is not None and set(c) >= {"value", "unit", "cores", "kind", "sample"} and c["kind"] in ("reference", "port")
         assert abs(d["value"] - 1000.0 / d["ms_per_step"]) < 0.5
 
 
