@@ -289,6 +289,9 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
     consumer_sync();
 }
 
+// ACT: act-order matrices present; TP: tensor parallel.  Compile-time so that the common kernel (neither) carries none of their
+// address arithmetic, branches or code (the runtime-flag version of the same source was 10 % slower on the plain 7B step).
+template <bool ACT, bool TP>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);      // nst x STAGE_STRIDE: pipeline g owns stages [g * depth, (g + 1) * depth)
     // staging slot 0: spt_max K stages; act-order adds slot 1 (H / 128 stages: only the multi-matrix phases, whose K is H, need it --
     // the two matrices a CTA's range can touch have different x_maps)
-    const int xstages = a.spt_max + (a.act ? a.H / TILE : 0);
+    const int xstages = a.spt_max + (ACT ? a.H / TILE : 0);
     const uint32_t xs_slot = (uint32_t)a.spt_max * 256u, seg_slot = (uint32_t)a.spt_max * 32u;
     unsigned char* xs = ring + (size_t)nst * STAGE_STRIDE;                            // xstages x 16 k8-rows x 16 B: quantised x planes by K stage
     unsigned char* segt = xs + (size_t)xstages * 256;                                  // xstages x 4 x {sum x_q, x scale}
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         unsigned long long v;
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
         s_base = v - v % (unsigned long long)G;          // at most G - 1 CTAs of THIS launch can have arrived already
-        s_base_x = a.tp_world > 1 ? (unsigned long long)__ldcg(a.launch_ctr) : 0ull;
+        s_base_x = TP ? (unsigned long long)__ldcg(a.launch_ctr) : 0ull;
     }
     consumer_sync();
     unsigned long long target = s_base + (unsigned long long)G;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     // with cp.async BEFORE the grid barrier (no registers held), so the phase prologue is left with one L2 round trip (the
     // accumulator) instead of two.  Slot r of wnorm holds the weights of row r of the staging order.
     auto preload_norm = [&](const half* nw, const Phase& p) {
-        if (a.act) return;                                    // act-order: the getter gathers the weights itself
+        if (ACT) return;                                    // act-order: the getter gathers the weights itself
         const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
         const int n = min(u1 - u0, p.spt), s0 = u1 > u0 ? u0 % p.spt : 0;
         for (int r = tid; r < n * 16; r += DS_CONSUMERS) {
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
     preload_norm(a.layers[0].ln1, phase_of(a, PH_QKV, G));
     grid_barrier(a.bar, target, (unsigned)G, tid);
-    if (a.tp_world > 1 && cta == 0 && tid == 0) *a.launch_ctr = (unsigned)s_base_x + 1u;      // every CTA has read it (it is past the barrier)
+    if (TP && cta == 0 && tid == 0) *a.launch_ctr = (unsigned)s_base_x + 1u;      // every CTA has read it (it is past the barrier)
 
     // ---- residual add (fp16(x + fp32 delta), the rounding point of q4_matmul's no_zero epilogue) + row factor of the RMS norm ----
     auto residual_and_norm = [&](const float* delta, const uint2* slots = nullptr, unsigned epoch = 0u) -> float {
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             if (delta) {
                 const float4 own0 = ldcg4(delta + i * 8), own1 = ldcg4(delta + i * 8 + 4);
                 float4 d0 = own0, d1 = own1;
-                if (slots) {
+                if (TP && slots) {
                     // tensor parallel: the sum over ALL ranks' partials in rank order (bitwise identical on every rank); the peers'
                     // partials sit in this rank's slots as {value, epoch} pairs, polled until the epoch of this (layer, phase) shows up
                     d0 = make_float4(0.f, 0.f, 0.f, 0.f); d1 = d0;
@@ -545,9 +548,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     auto stage_phase = [&](const Phase& p, int u0, int u1, auto make_get) {
         if (u1 <= u0) return;
         const int per_mat = p.tpm * p.spt;
-        const int mi0 = u0 / per_mat, mi1 = a.act ? (u1 - 1) / per_mat : mi0;
+        const int mi0 = u0 / per_mat, mi1 = ACT ? (u1 - 1) / per_mat : mi0;
         for (int mi = mi0; mi <= mi1; mi++) {
-            const int ua = a.act ? max(u0, mi * per_mat) : u0, ub = a.act ? min(u1, (mi + 1) * per_mat) : u1;
+            const int ua = ACT ? max(u0, mi * per_mat) : u0, ub = ACT ? min(u1, (mi + 1) * per_mat) : u1;
             stage_x(ua % p.spt, min(ub - ua, p.spt), p.spt, make_get(p.mat0 + mi), mi - mi0);
         }
     };
@@ -594,13 +597,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const uint32_t sc_lane = (uint32_t)(META_SC + lane_col * 2), zq_lane = (uint32_t)(META_ZQ + (lane_col >> 3) * 4);
         const uint32_t zshift = (uint32_t)((lane_col & 4) * 4);
         const uint32_t seg_a = smem_u32(segt);
-        const int mi_first = a.act ? (u0 / p.spt) / p.tpm : 0;       // staging slot of a tile = its matrix - the first matrix of the CTA's range
-        uint32_t xoff = a.act ? (uint32_t)(cur_tile / p.tpm - mi_first) * xs_slot : 0u, soff = a.act ? (uint32_t)(cur_tile / p.tpm - mi_first) * seg_slot : 0u;
+        const int mi_first = ACT ? (u0 / p.spt) / p.tpm : 0;       // staging slot of a tile = its matrix - the first matrix of the CTA's range
+        uint32_t xoff = ACT ? (uint32_t)(cur_tile / p.tpm - mi_first) * xs_slot : 0u, soff = ACT ? (uint32_t)(cur_tile / p.tpm - mi_first) * seg_slot : 0u;
         bool ready = mbar_try(full0 + ls * 8, par);
         for (; u < u1; u += 4) {
             if (tile != cur_tile) {
                 flush_tile(); cur_tile = tile;
-                if (a.act) { const uint32_t sl = (uint32_t)(tile / p.tpm - mi_first); xoff = sl * xs_slot; soff = sl * seg_slot; }
+                if (ACT) { const uint32_t sl = (uint32_t)(tile / p.tpm - mi_first); xoff = sl * xs_slot; soff = sl * seg_slot; }
             }
             const uint32_t tok = mbar_wait_tok(full0 + ls * 8, par, ready);
             const int ls_cur = ls;
@@ -729,9 +732,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             stamp(l, 0);
             if (l > 0) zero_share(a.acc_gu, 2 * a.I);
-            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && !a.tp_reduce && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
+            rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (TP && !a.tp_reduce && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
             stamp(l, 15);
-            if (!a.act) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
+            if (!ACT) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
             else stage_phase(p, u0, u1, [&](int m) { return norm_get_map(L->ln1, rm, L->xmap[m]); });
             consumer_sync();
             stamp(l, 1);
@@ -934,7 +937,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                 for (int i = 0; i < 4; i++) hh[i] = __floats2half2_rn(ov[2 * i] * inv, ov[2 * i + 1] * inv);
                 return r;
             };
-            if (!a.act) {
+            if (!ACT) {
                 // stage k of o_proj is head k: the CTA combines exactly the heads its K range needs
                 if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 { return combine8(k8 >> 4, (k8 & 15) * 8); });
             } else {
@@ -962,7 +965,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             preload_norm(L->ln2, phase_of(a, PH_GU, G));
             stamp(l, 7);
         }
-        if (a.tp_world > 1) push_partial(a.acc_o, a.push_o, epoch0 + 2u * l, l, 16);
+        if (TP) push_partial(a.acc_o, a.push_o, epoch0 + 2u * l, l, 16);
         else grid_barrier(a.bar, target, (unsigned)G, tid);
         stamp(l, 8);
 
@@ -970,8 +973,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
             const Phase p = phase_of(a, PH_GU, G);
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
-            rm = residual_and_norm(a.acc_o, (a.tp_world > 1 && !a.tp_reduce) ? a.slots_o : nullptr, epoch0 + 2u * l);
-            if (!a.act) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
+            rm = residual_and_norm(a.acc_o, (TP && !a.tp_reduce) ? a.slots_o : nullptr, epoch0 + 2u * l);
+            if (!ACT) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
             else stage_phase(p, u0, u1, [&](int m) { return norm_get_map(L->ln2, rm, L->xmap[m]); });
             consumer_sync();
             stamp(l, 9);
@@ -987,7 +990,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const Phase p = phase_of(a, PH_DOWN, G);
             const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
             zero_share(a.acc_o, a.H);
-            if (!a.act) {
+            if (!ACT) {
                 if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
                     // silu(gate) * up on the fp16-rounded projections (q4_mlp.cu:27-36,46-88)
                     const float4 g0 = ldcg4(a.acc_gu + k8 * 8), g1 = ldcg4(a.acc_gu + k8 * 8 + 4);
@@ -1020,13 +1023,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             if (l + 1 < a.n_layers) preload_norm(a.layers[l + 1].ln1, phase_of(a, PH_QKV, G));
             stamp(l, 13);
         }
-        if (a.tp_world > 1) push_partial(a.acc_d, a.push_d, epoch0 + 2u * l + 1u, l, 18);
+        if (TP) push_partial(a.acc_d, a.push_d, epoch0 + 2u * l + 1u, l, 18);
         else grid_barrier(a.bar, target, (unsigned)G, tid);
         stamp(l, 14);
     }
 
     // ========================================================= HEAD ==========================================================
-    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr, (a.tp_world > 1 && !a.tp_reduce && a.n_layers > 0) ? a.slots_d : nullptr, epoch0 + 2u * (a.n_layers - 1) + 1u);
+    rm = residual_and_norm(a.n_layers > 0 ? a.acc_d : nullptr, (TP && !a.tp_reduce && a.n_layers > 0) ? a.slots_d : nullptr, epoch0 + 2u * (a.n_layers - 1) + 1u);
     if (a.x_out && cta == 0)
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
     if (a.lm_head) {
@@ -1101,6 +1104,12 @@ struct exl_decode_plan
     int grid = 0;
 };
 
+static const void* step_kernel_for(bool act, bool tp)
+{
+    if (act) return tp ? (const void*)decode_step_kernel<true, true> : (const void*)decode_step_kernel<true, false>;
+    return tp ? (const void*)decode_step_kernel<false, true> : (const void*)decode_step_kernel<false, false>;
+}
+
 static int plan_fail(exl_decode_plan* p, int rc)
 {
     if (p) {
@@ -1174,10 +1183,11 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     const int nst = 4 * depth;
     p->smem = fixed - 1024 + (size_t)nst * STAGE_STRIDE;
     if ((size_t)H * 2 > (size_t)a.spt_max * 256) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: internal: head staging does not fit"));
-    cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    const void* kfn = step_kernel_for(any_act, d->tp_world > 1);
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (e != cudaSuccess) return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: smem attribute (%zu B): %s", p->smem, cudaGetErrorString(e)));
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel, DS_THREADS, p->smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, DS_THREADS, p->smem);
     if (e != cudaSuccess || per_sm < 1) return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: kernel does not fit an SM (smem %zu)", p->smem));
     p->grid = ds->num_sms;
     if (const char* eg = getenv("EXL_DS_GRID")) { int v = atoi(eg); if (v >= 1 && v <= ds->num_sms) p->grid = v; }
@@ -1295,7 +1305,8 @@ extern "C" int exl_decode_step(exl_decode_plan* p, const void* x_in, int past_le
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;      // all CTAs co-resident: the grid barrier relies on it
     cfg.gridDim = dim3((unsigned)p->grid); cfg.blockDim = dim3(DS_THREADS); cfg.dynamicSmemBytes = p->smem; cfg.stream = (cudaStream_t)stream_;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_kernel, a);
+    void* kargs[1] = {(void*)&a};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, step_kernel_for(a.act != 0, a.tp_world > 1), kargs);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return exl_set_err(EXL_ERR_CUDA, "launch of decode_step_kernel failed: %s (grid %d, smem %zu)", cudaGetErrorString(e), p->grid, p->smem);
     return EXL_OK;
