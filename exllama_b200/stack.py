@@ -25,7 +25,31 @@ ext = cuda_ext.exllama_ext
 from .shapes import SHAPES, LlamaShape  # noqa: E402,F401  (re-exported)
 
 
-def synth_q4_device(K, N, groupsize, device, gen, act_order=False, scale_lo=None, scale_hi=None):
+class _Arena:
+    """One device allocation handed out in 256-byte aligned slices, in request order (a loader that maps one checkpoint file
+    region): the GPTQ tensors of a stack then sit back to back in HBM instead of wherever the caching allocator had room."""
+
+    def __init__(self, nbytes, device):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.off = 0
+
+    def take(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= d
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        v = self.buf[self.off:self.off + nb].view(dtype).view(*shape)
+        self.off += (nb + 255) & ~255
+        return v
+
+    @staticmethod
+    def q4_bytes(K, N, groupsize):
+        G = K // groupsize
+        r = lambda b: (b + 255) & ~255
+        return r(K // 8 * N * 4) + r(G * (N // 8) * 4) + r(G * N * 2)
+
+
+def synth_q4_device(K, N, groupsize, device, gen, act_order=False, scale_lo=None, scale_hi=None, arena=None):
     """Random GPTQ tensor set on the device, shaped like a real checkpoint: uniform 4-bit weights, zero points in the middle of
     the range (stored nibble 6 or 7, i.e. z + 1 = 7 or 8, mean 7.5 = the mean nibble: zero-mean weights, as GPTQ produces for
     symmetric weight groups.  A mean offset of even one quantisation step gives every matrix a DC gain of ~scale * K >> 1 and a
@@ -36,12 +60,19 @@ def synth_q4_device(K, N, groupsize, device, gen, act_order=False, scale_lo=None
         scale_hi = 2.3e-3 * (4096.0 / K) ** 0.5
     if scale_lo is None:
         scale_lo = 0.1 * scale_hi
-    qweight = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=device, generator=gen)
+    if arena is not None:
+        qweight = arena.take((K // 8, N), torch.int32)
+        torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=device, generator=gen, out=qweight)
+    else:
+        qweight = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=device, generator=gen)
     zn = torch.randint(6, 8, (G, N // 8, 8), dtype=torch.int64, device=device, generator=gen)
     shifts = (torch.arange(8, device=device, dtype=torch.int64) * 4)
     qz = (zn << shifts).sum(-1)                                   # 8 nibbles per word, nibble n % 8 of word [g, n / 8]
     qzeros = torch.where(qz >= 2**31, qz - 2**32, qz).to(torch.int32)
     scales = (torch.rand((G, N), device=device, generator=gen) * (scale_hi - scale_lo) + scale_lo).half()
+    if arena is not None:
+        qzeros = arena.take((G, N // 8), torch.int32).copy_(qzeros)
+        scales = arena.take((G, N), torch.float16).copy_(scales)
     g_idx = None
     if act_order:
         perm = torch.randperm(K, device=device, generator=gen)
@@ -98,9 +129,12 @@ class DecodeStack:
         with torch.cuda.device(self.device):
             ext.set_tuning_params(8, 2, 8, False, False, False, False, False, False)
             self.layers = []
+            per_layer = (3 * _Arena.q4_bytes(h, hq, groupsize) + _Arena.q4_bytes(hq, h, groupsize) + 2 * _Arena.q4_bytes(h, il, groupsize) +
+                         _Arena.q4_bytes(il, h, groupsize))
+            self.arena = _Arena(per_layer * self.n_layers, self.device)
             for _ in range(self.n_layers):
                 L = Layer()
-                mk = lambda K, N: Q4Linear(*synth_q4_device(K, N, groupsize, self.device, gen, act_order), self.dev_index)
+                mk = lambda K, N: Q4Linear(*synth_q4_device(K, N, groupsize, self.device, gen, act_order, arena=self.arena), self.dev_index)
                 L.q, L.k, L.v = mk(h, hq), mk(h, hq), mk(h, hq)
                 L.o = mk(hq, h)
                 L.gate, L.up = mk(h, il), mk(h, il)

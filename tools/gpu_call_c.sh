@@ -1,5 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-rm -f gpurun_out/c_trace.log
-EXL_DS_DEBUG=0 timeout 200 python tools/step_trace.py --ctx 1920 --layers 3 >> gpurun_out/c_trace.log 2>&1
-grep -v Warning gpurun_out/c_trace.log | tail -2 | cut -c1-600
+for v in m1 m2 m3 m4 f5ef730; do
+EXL_B200_LIB=$PWD/exllama_b200/libexl_b200_$v.so timeout 300 python tools/step_bench.py --model 7b --ctx 1920 --no-per-op 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', d['fused_ms'])"
+done
