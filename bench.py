@@ -345,12 +345,14 @@ def main():
         launches_per_step = launches_per_op
         mode = "per-op kernels, " + ("CUDA graph" if graph is not None else "eager")
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        # one GPU's clocks (rank 0's); started before the warm-up steps (the same kernel under the same load) so that the ~100 ms
+        # timed region is covered by more than a couple of 50 ms samples; stopped right after the timed region
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # one GPU's clocks (rank 0's) are reported; the other ranks start nothing beside their launch loop
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.cudart().cudaProfilerStart()          # no-op unless run under `ncu --profile-from-start off`
     e0.record()

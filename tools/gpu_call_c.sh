@@ -1,4 +1,8 @@
 #!/bin/bash
-for v in m1 m2 m3 m4 f5ef730; do
-EXL_B200_LIB=$PWD/exllama_b200/libexl_b200_$v.so timeout 300 python tools/step_bench.py --model 7b --ctx 1920 --no-per-op 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', d['fused_ms'])"
-done
+mkdir -p gpurun_out
+timeout 200 python bench.py --model 13b --act-order --steps 32 --warmup 4 --no-prefill --no-cpu-baseline > gpurun_out/r2_bench_13b_act_final.json 2> gpurun_out/r2_bench_13b_act_final.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.loads([l for l in open("gpurun_out/r2_bench_13b_act_final.json") if l.startswith("{")][-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["step_parity"], d["decode_per_op_graph"]["value"])
+PY
