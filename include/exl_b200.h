@@ -152,7 +152,12 @@ int exl_q4_mlp(void* x, const void* rms_norm_weight, float epsilon,
 
 /* Single-query attention over the KV cache, replacing the torch ops of ExLlamaAttention.fused (model.py:372-409):
    out[h, :] = softmax(q[h] . K[kvh(h), 0:seq]^T / sqrt(head_dim)) . V[kvh(h), 0:seq]      (fp32 arithmetic, fp16 in/out)
-   q, out: half [num_heads * head_dim] (one token); caches: half [num_kv_heads, max_seq_len, head_dim]; head_dim == 128. */
+   q, out: half [num_heads * head_dim] (one token); caches: half [num_kv_heads, max_seq_len, head_dim]; head_dim == 128.
+   Ordering precondition: the kernel is launched with programmatic stream serialisation and waits (griddepcontrol.wait)
+   only on the kernel launched IMMEDIATELY BEFORE it on `stream`.  q and the cache rows of position seq_len-1 must
+   therefore be written either by that preceding kernel (as exl_q4_attn does) or by work that completed earlier; memcpys
+   and kernels on `stream` are ordered as usual, writers on OTHER streams need an event wait recorded before the
+   preceding kernel. */
 int exl_decode_attn(const void* q, const void* key_cache, const void* value_cache, void* out,
                     int num_heads, int num_kv_heads, int head_dim, int seq_len, int max_seq_len, void* stream);
 
@@ -161,8 +166,9 @@ int exl_decode_attn(const void* q, const void* key_cache, const void* value_cach
 /* Everything ExLlama.forward does for one new token of one sequence (model.py:1053-1077: per layer ExLlamaAttention.fused
    :322-417 and ExLlamaMLP.fused :238-263, then the final norm and lm_head), in one cooperative launch -- see
    exllama_b200/csrc/decode_step.cu.  The plan borrows every pointer in the descriptor (weights, norms, caches, tables);
-   they must stay valid and fixed for the plan's lifetime.  Restrictions: head_dim 128, kv_heads == heads, no act-order,
-   groupsize 32 * 2^n (or one group), widths multiples of 128; anything else -> EXL_ERR_ARG (use the per-op entry points). */
+   they must stay valid and fixed for the plan's lifetime.  Restrictions: head_dim 128, kv_heads == heads, groupsize 32 * 2^n
+   (or one group), widths multiples of 128, act-order (g_idx) matrices only with tp_world == 1; anything else ->
+   EXL_ERR_ARG (use the per-op entry points). */
 typedef struct exl_decode_plan exl_decode_plan;
 typedef struct exl_decode_desc {
     int n_layers, num_heads, head_dim, max_seq_len, vocab;
@@ -176,8 +182,9 @@ typedef struct exl_decode_desc {
     const void* final_norm;              /* half [hidden] or NULL */
     const void* lm_head;                 /* half [vocab, hidden] (nn.Linear weight, model.py:845-846) or NULL: no head */
     /* tensor parallel (0 / 1 = single GPU): this rank's column shards of q, k, v, gate, up (num_heads = LOCAL heads) and
-       row shards of o, down; norms, tables, x and the head replicated.  The row-parallel partials are reduced into every rank's
-       accumulator over NVLink inside the same kernel (peer-memory atomics + a cross-GPU barrier): no separate collective. */
+       row shards of o, down; norms, tables, x and the head replicated.  The row-parallel partials are exchanged over NVLink inside the same
+       kernel ({value, launch-epoch} 8-byte stores into every peer's slot buffer, polled by the consumer and summed in rank order):
+       no separate collective, no cross-GPU barrier. */
     int tp_rank, tp_world;
 } exl_decode_desc;
 
@@ -191,7 +198,7 @@ int exl_decode_plan_ipc_import(exl_decode_plan* plan, const void* handles, int w
 int exl_decode_plan_info(const exl_decode_plan* plan, int* grid, int* ring_stages, int64_t* smem_bytes, int64_t* barriers_per_step);
 
 /* Bring-up aid: with EXL_DS_TRACE=1 in the environment when the plan is created, every CTA stamps %globaltimer at its phase
-   boundaries of the first 4 layers; this copies the [grid][4][16] stamps of the last launch to the host. */
+   boundaries of the first 4 layers; this copies the [grid][4][24] stamps of the last launch to the host. */
 int exl_decode_plan_trace(exl_decode_plan* plan, unsigned long long* out_host, int64_t capacity);
 
 /* One token: x_in half [hidden] (the embedding row), attends over cache rows [0, past_len) plus the new row, which it
