@@ -18,7 +18,7 @@ LIB_SO = os.path.join(HERE, "libexl_b200.so")
 EXT_SO = os.path.join(HERE, "exllama_ext.so")
 
 CU_SOURCES = ["capi.cu", "q4_gemv.cu", "q4_matrix.cu", "elementwise.cu", "half_matmul.cu", "q4_gemm_tc.cu", "decode_attn.cu", "decode_step.cu"]
-HEADERS = ["exl_common.cuh", os.path.join("..", "..", "include", "exl_b200.h")]
+HEADERS = ["exl_common.cuh", "decode_step_sched.h", os.path.join("..", "..", "include", "exl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]

@@ -227,6 +227,11 @@ static int q4_matmul_dispatch(ExlDevice* ds, const half* x, int M, const exl_q4_
 {
     if (M <= 0) return EXL_OK;
     int path = force_path;
+    // the skinny kernel streams 32-row x 32-column boxes and quantises x per 32 * 2^n-row group (q4_gemv.cu: exl_gemv_launch); any other
+    // shape takes the general route (reconstruct + cuBLAS, the reference's own large-M path, q4_matmul.cu:301-344) instead of failing
+    const int gs32 = w->groupsize / 32;
+    const bool gemv_ok = w->K % 32 == 0 && w->N % 32 == 0 && (w->groups == 1 || (w->groupsize % 32 == 0 && (gs32 & (gs32 - 1)) == 0));
+    if (path == 0 && !gemv_ok) path = 3;
     if (path == 0) {
         // M <= 8: one skinny pass.  8 < M <= 48: still HBM-bound, a few skinny passes (each re-streams the packed weights,
         // 0.5 B / weight) beat a tensor-core tile that is mostly padding.  Above: tcgen05 fused-dequant GEMM.

@@ -10,12 +10,13 @@
 // (model.py:383-409), q4_matmul += residual (q4_attn.cu:206-228), rms_norm + 2 x q4_matmul + silu_mul + q4_matmul += residual
 // (q4_mlp.cu:100-199), and at the end model.py:1069-1077 (norm + lm_head).
 //
-// Structure (one CTA per SM, 16 consumer warps + 1 producer warp):
-//  * The PRODUCER warp walks a static schedule of 8 KB "stages" through a shared-memory ring with full/empty mbarriers and
-//    never waits for a grid barrier: weights (2-D TMA boxes of the packed qweight + 1-D bulk copies of the stage's scale /
-//    zero rows), KV-cache rows older than the current token (bulk copies) and lm_head rows do not depend on activations, so
-//    up to NST x 8 KB per SM (~24 MB chip-wide) of the NEXT phase is already in flight while the consumers are in a barrier
-//    or in a phase prologue.  HBM stays busy across phase and layer boundaries -- the thing separate launches could not do.
+// Structure (one CTA per SM; 16 consumer warps + 4 producer warps = 4 pipelines of {1 producer, 4 consumer warps, own ring slice}):
+//  * The PRODUCER warps walk a static schedule of 8 KB "stages" (stage j of the CTA belongs to pipeline j & 3) through a
+//    shared-memory ring with full/empty mbarriers and never wait for a grid barrier: weight units (ONE 3-D TMA op for the
+//    8 KB of packed qweight + one 2-D op each for the unit's scale and zero rows), KV-cache rows older than the current token
+//    (bulk copies) and lm_head rows do not depend on activations, so up to 4 x depth x 8 KB per SM (~19 MB chip-wide) of the
+//    NEXT phase is already in flight while the consumers are in a barrier or in a phase prologue.  HBM stays busy across
+//    phase and layer boundaries -- the thing separate launches could not do.
 //  * Work of a GEMV phase = (128-column tile) x (128-row K stage) units, flattened tile-major and cut into G equal contiguous
 //    ranges (G = grid size): every SM streams the same number of bytes whatever the matrix shapes (65B gate/up: 172 tiles on
 //    148 SMs is no longer a problem).  A warp accumulates its 32 columns over the stages it sees and, at a tile boundary,
@@ -32,31 +33,29 @@
 //  * HEAD: lm_head [vocab, hidden] fp16 streamed as 8 KB stages, fp32 dot products, fp32 logits by red.global.add.
 //
 // Restrictions (checked on the host; anything else uses the per-op kernels): head_dim 128, kv_heads == heads, groupsize 32 * 2^n
-// (or one group), no act-order, widths multiples of 128.  Every wait is bounded by wall time and traps on expiry.
+// (or one group), widths multiples of 128, act-order only without tensor parallelism (template flag ACT: x is gathered through
+// each matrix's x_map while it is staged).  Tensor parallel (template flag TP): the row-parallel partials are exchanged by
+// {value, epoch} stores into the peers' memory, see StepArgs.  Every wait is bounded by wall time and traps on expiry.
 #include "exl_common.cuh"
+#include "decode_step_sched.h"
 #include <cstring>
 #include <type_traits>
 #include <vector>
 
 namespace {
 
+using namespace ds_sched;                        // TILE, W_BYTES, STAGE_STRIDE, PART_LD, MAX_DEPTH, PH_*, Phase, phase_of, range_lo, share_lo, cta_of
+
 constexpr int DS_CONSUMERS = 512;                // 16 consumer warps = 4 pipelines x 4 column-warps
 constexpr int DS_NCW = DS_CONSUMERS / 32;
 constexpr int DS_NPW = 4;                        // producer warps, one per pipeline
 constexpr int DS_THREADS = DS_CONSUMERS + 32 * DS_NPW;
-constexpr int TILE = 128;                        // columns per tile == K rows per stage
-constexpr int W_BYTES = 8192;                    // packed weights of one unit: 16 k8-rows x 128 columns x 4 B
 constexpr int BOX_BYTES = 2048;                  // one column group of the unit: 16 k8-rows x 32 columns, SWIZZLE_128B
 constexpr int META_SC = W_BYTES;                 // up to 4 group rows of 128 fp16 scales
 constexpr int META_ZQ = W_BYTES + 1024;          // up to 4 group rows of 128 zero nibbles
-constexpr int STAGE_STRIDE = W_BYTES + 2048;     // keeps every stage 1 KB aligned (swizzle atom)
-constexpr int PART_LD = 132;                     // attention partial: o[128], m, l, pad
 constexpr int MAX_LAYERS = 128;
-constexpr int MAX_DEPTH = 6;                     // ring stages per pipeline
 constexpr int TRACE_LAYERS = 4;
 constexpr unsigned long long WAIT_NS = 4000000000ull;   // any single wait longer than this aborts the launch
-
-enum { PH_QKV = 0, PH_ATT = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_HEAD = 5 };
 
 struct alignas(64) LayerDesc
 {
@@ -232,38 +231,6 @@ __device__ __forceinline__ float row_absmax(const uint4& hv)
     #pragma unroll
     for (int i = 0; i < 4; i++) { const float2 f = __half22float2(__habs2(h[i])); mx = fmaxf(mx, fmaxf(f.x, f.y)); }
     return mx;
-}
-
-// contiguous share of n items for CTA c of G
-__device__ __forceinline__ int share_lo(long long n, int c, int G) { return (int)(n * c / G); }
-// share of CTA c in a phase that p_G <= G CTAs take part in: [lo, hi), empty for c >= p_G
-__device__ __forceinline__ int range_lo(long long n, int c, int pG) { return c >= pG ? (int)n : (int)(n * c / pG); }
-// the CTA whose share contains item u (inverse of share_lo)
-__device__ __forceinline__ int cta_of(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
-
-struct Phase { int kind, U, spt, tpm, nmat, mat0, N, G; float* acc; };     // G: CTAs that take part in the phase     // tpm: tiles per matrix (ATT: units per head)
-
-__device__ __forceinline__ Phase phase_of(const StepArgs& a, int kind, int grid)
-{
-    Phase p; p.kind = kind; p.acc = nullptr; p.G = grid; p.spt = 0; p.tpm = 0; p.nmat = 0; p.mat0 = 0; p.N = 0; p.U = 0;
-    if (kind == PH_QKV)       { p.spt = a.H / TILE;  p.N = a.HQ; p.nmat = 3; p.mat0 = 0; p.acc = a.acc_qkv; }
-    else if (kind == PH_O)    { p.spt = a.HQ / TILE; p.N = a.H;  p.nmat = 1; p.mat0 = 3; p.acc = a.acc_o; }
-    else if (kind == PH_GU)   { p.spt = a.H / TILE;  p.N = a.I;  p.nmat = 2; p.mat0 = 4; p.acc = a.acc_gu; }
-    else if (kind == PH_DOWN) { p.spt = a.I / TILE;  p.N = a.H;  p.nmat = 1; p.mat0 = 6; p.acc = a.acc_d; }
-    if (kind == PH_ATT) {
-        const int nch = (a.past_len + 15) >> 4;
-        p.tpm = nch > 0 ? nch : 1;                          // units per head (one empty unit when there is no history)
-        p.U = a.heads * p.tpm;
-        // at most ~7 CTAs per head: the O prologue combines one partial per CTA and head (two rounds of 4 loads); with few heads
-        // per GPU (tensor parallel) the rest of the grid sits this phase out -- its bytes are small then
-        if (a.heads * 7 < grid) p.G = a.heads * 7;
-    } else if (kind == PH_HEAD) {
-        p.U = a.lm_head ? (int)(((long long)a.vocab * a.H * 2 + W_BYTES - 1) / W_BYTES) : 0;
-    } else {
-        p.tpm = p.N / TILE;
-        p.U = p.nmat * p.tpm * p.spt;
-    }
-    return p;
 }
 
 // Grid-wide barrier for the consumer threads of all CTAs: one monotonic 64-bit arrival counter (never reset, so graph replays
@@ -1091,6 +1058,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     }
 }
 
+// Attention partial table -> neutral partials (o = 0, m = -inf, l = 0).  Launched by exl_decode_step before a step whose attention
+// phase leaves CTAs idle inside a head's CTA range (short contexts, decode_step_sched.h: att_needs_reset): the slots those CTAs would
+// have written must not carry partials of an earlier, longer context into the O prologue's combine.
+__global__ void att_part_reset_kernel(float* __restrict__ att_part, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) att_part[i] = (i % PART_LD) == 128 ? -INFINITY : 0.f;
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -1173,16 +1149,15 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     a.eps = d->rms_eps; a.sin = (const half*)d->sin; a.cos = (const half*)d->cos;
     a.final_norm = (const half*)d->final_norm; a.lm_head = (const half*)d->lm_head; a.vocab = d->lm_head ? d->vocab : 0;
     if (d->lm_head && (!d->final_norm || d->vocab % 4)) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: lm_head needs final_norm and vocab %% 4 == 0"));
-    a.spt_max = (H > I ? H : I) / TILE; if (HQ / TILE > a.spt_max) a.spt_max = HQ / TILE;
+    a.spt_max = spt_max_for(H, HQ, I);
     a.act = any_act ? 1 : 0;
     if (any_act && d->tp_world > 1)
         return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: act-order matrices under tensor parallelism are not supported by the fused step (o_proj needs the all-gathered attention output): use the per-op path"));
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
-    const size_t fixed = 1024 + (size_t)(a.spt_max + (any_act ? H / TILE : 0)) * (256 + 32) + (size_t)H * 2 + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + (size_t)H * 2 /* wnorm */ + 1024 /* static */;
-    int depth = (int)(((size_t)dev_smem - fixed) / STAGE_STRIDE) / 4;
+    const size_t fixed = smem_fixed_bytes(H, HQ, I, any_act);
+    int depth = ring_depth_for((size_t)dev_smem, fixed);
     if (const char* e = getenv("EXL_DS_DEPTH")) { int v = atoi(e); if (v >= 1 && v < depth) depth = v; }
-    if (depth > MAX_DEPTH) depth = MAX_DEPTH;
     if (depth < 2) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: model too wide for the shared-memory plan (%d ring stages per pipeline)", depth));
     if (d->num_heads > ds->num_sms) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: more heads (%d) than SMs", d->num_heads));
     a.depth = depth;
@@ -1197,7 +1172,7 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     if (e != cudaSuccess || per_sm < 1) return plan_fail(p, exl_set_err(EXL_ERR_CUDA, "decode_plan: kernel does not fit an SM (smem %zu)", p->smem));
     p->grid = ds->num_sms;
     if (const char* eg = getenv("EXL_DS_GRID")) { int v = atoi(eg); if (v >= 1 && v <= ds->num_sms) p->grid = v; }
-    a.att_slots = (p->grid < 7 * d->num_heads ? p->grid / d->num_heads : 7) + 2;
+    a.att_slots = att_slots_for(p->grid, d->num_heads);
     // scratch: accumulators | attention partials | barrier
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -1305,6 +1280,15 @@ extern "C" int exl_decode_step(exl_decode_plan* p, const void* x_in, int past_le
     DeviceGuard guard(p->device);
     StepArgs a = p->args;
     a.x_in = (const half*)x_in; a.x_out = (half*)x_out; a.logits = (float*)logits; a.past_len = past_len;
+    if (att_needs_reset(a.heads, past_len, p->grid)) {
+        // short context: some CTAs inside a head's CTA range own no attention unit in this launch (stateless test, so a captured
+        // CUDA graph -- past_len is baked into it -- replays the same decision)
+        const int n = a.heads * a.att_slots * PART_LD;
+        att_part_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(a.att_part, n);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t er = cudaGetLastError();
+        if (er != cudaSuccess) return exl_set_err(EXL_ERR_CUDA, "launch of att_part_reset_kernel failed: %s", cudaGetErrorString(er));
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute at[1];

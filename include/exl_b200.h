@@ -153,11 +153,13 @@ int exl_q4_mlp(void* x, const void* rms_norm_weight, float epsilon,
 /* Single-query attention over the KV cache, replacing the torch ops of ExLlamaAttention.fused (model.py:372-409):
    out[h, :] = softmax(q[h] . K[kvh(h), 0:seq]^T / sqrt(head_dim)) . V[kvh(h), 0:seq]      (fp32 arithmetic, fp16 in/out)
    q, out: half [num_heads * head_dim] (one token); caches: half [num_kv_heads, max_seq_len, head_dim]; head_dim == 128.
-   Ordering precondition: the kernel is launched with programmatic stream serialisation and waits (griddepcontrol.wait)
-   only on the kernel launched IMMEDIATELY BEFORE it on `stream`.  q and the cache rows of position seq_len-1 must
-   therefore be written either by that preceding kernel (as exl_q4_attn does) or by work that completed earlier; memcpys
-   and kernels on `stream` are ordered as usual, writers on OTHER streams need an event wait recorded before the
-   preceding kernel. */
+   Ordering precondition (programmatic dependent launch): the kernel loads cache rows 0 .. seq_len-2 BEFORE it waits for
+   the kernel launched immediately before it on `stream` (griddepcontrol.wait); only q and row seq_len-1 are read after
+   the wait.  A preceding kernel that releases its dependents early (griddepcontrol.launch_dependents -- this library's
+   GEMV kernels, i.e. exl_q4_attn / exl_q4_matmul with <= 8 rows, do) may therefore produce q and cache row seq_len-1, as
+   exl_q4_attn with q_len 1 does, but must not write older cache rows: after a multi-token exl_q4_attn (q_len 2..8) put
+   any other kernel or a stream synchronisation before this call.  Kernels that never release early (torch ops, copies)
+   are ordered as usual. */
 int exl_decode_attn(const void* q, const void* key_cache, const void* value_cache, void* out,
                     int num_heads, int num_kv_heads, int head_dim, int seq_len, int max_seq_len, void* stream);
 

@@ -122,6 +122,34 @@ def test_fused_step_sequence_and_graph(oracle):
     st.dplan.close(); st.close()
 
 
+def test_fused_step_short_context_after_long_one(oracle):
+    """ONE plan: a long context first (every slot of the attention-partial table gets written), then short contexts where some CTAs
+    inside a head's CTA range own no attention unit (tests/test_decode_schedule.py: the hazard the CPU schedule proof found).
+    Partials of the long context must not leak into the short contexts' softmax combine: exl_decode_step resets the table first."""
+    import torch
+    from exllama_b200 import capi
+    st = _mk_stack(1024, 2816, 2, 8, 128, 256, seed=7)
+    st.make_plan()
+    g = torch.Generator(device="cuda"); g.manual_seed(21)
+    snap = [(kc.clone(), vc.clone()) for kc, vc in zip(st.key_cache, st.value_cache)]
+
+    def restore():
+        for (kc, vc), (k0, v0) in zip(zip(st.key_cache, st.value_cache), snap):
+            kc.copy_(k0); vc.copy_(v0)
+    # 8 heads -> 56 CTAs take part in the attention phase; 16-position chunks: contexts 17 .. 96 leave some of them idle
+    for past, extra in [(200, 0), (37, 1), (17, 1), (100, 0), (49, 1), (3, 0), (96, 1), (200, 0)]:
+        x = (torch.randn((1, 1, 1024), device="cuda", generator=g) * 0.5).half()
+        ref = st.decode_step(x.clone(), past).clone()
+        restore()
+        n0 = capi.launch_count()
+        got = st.decode_step_fused(x, past).clone()
+        torch.cuda.synchronize()
+        assert capi.launch_count() - n0 == 1 + extra, (past, capi.launch_count() - n0)      # the table reset runs only where it is needed
+        restore()
+        assert_close_ref64(got.cpu().numpy().reshape(-1), ref.cpu().numpy().reshape(-1).astype(np.float64), rel=1.5e-2, rms=1.5e-2, what=f"logits at ctx {past}")
+    st.dplan.close(); st.close()
+
+
 def test_fused_step_7b_shape_long_context(oracle):
     """BASELINE shape (hidden 4096, inter 11008, 32 heads, vocab 32000) at ctx 1920, 2 layers: against the per-op path."""
     import torch

@@ -134,6 +134,20 @@ def test_recons_cublas_path(oracle, M, K, N, gs, act):
     assert_close_ref64(out.cpu().numpy(), ref, what="recons")
 
 
+@pytest.mark.parametrize("M,K,N,gs,act", [(1, 768, 256, 96, False), (5, 1152, 160, 192, True)])
+def test_skinny_unsupported_groupsize_takes_general_route(oracle, M, K, N, gs, act):
+    """A group size that is not 32 * 2^n cannot go through the skinny kernel; instead of an error the call takes the
+    reconstruct + cuBLAS route, which handles any GPTQ shape the reference's kernels handle."""
+    from exllama_b200 import capi
+    qw, qz, sc, g_idx = _mk(oracle, K, N, gs, act, seed=33)
+    x = oracle.synth_x(M, K, seed=8)
+    q4 = _q4(capi, qw, qz, sc, g_idx)
+    out = capi.q4_matmul(to_cuda(x), q4)
+    assert capi.last_q4_path() == "recons_cublas"
+    ref = oracle.ref64_with_act_order(x, qw, qz, sc, g_idx, recons=True)
+    assert_close_ref64(out.cpu().numpy(), ref, what=f"general route gs={gs}")
+
+
 TC_CASES = [(128, 1024, 512, 128, False), (200, 2048, 384, 32, True), (1, 512, 128, 64, False), (77, 4096, 1152, 128, True),
             (384, 1024, 1024, 1024, False), (130, 2816, 96, 128, False)]
 
