@@ -124,6 +124,6 @@ def test_attention_table_reset_is_confined_to_short_contexts(lib):
     rc, msg = check(lib, s.hidden, s.hidden, s.inter, s.heads, s.vocab, SMS, 0, 2047, False, c)
     assert rc == 0, msg
     assert c["gaps"] > 0                      # the hazard is real (found by this test before the reset existed) ...
-    assert 0 < c["resets"] <= 80              # ... and confined: 32 heads, 148 CTAs -> contexts 17 .. 16 * ceil(148 / 32) - 1
-    rc, msg = check(lib, s.hidden, s.hidden, s.inter, s.heads, s.vocab, SMS, 80, 2047, False, c)
+    assert c["resets"] == 48                  # ... and confined: 32 heads x nph units < 148 CTAs, nph >= 2 -> contexts 17 .. 64
+    rc, msg = check(lib, s.hidden, s.hidden, s.inter, s.heads, s.vocab, SMS, 65, 2047, False, c)
     assert rc == 0 and c["gaps"] == 0 and c["resets"] == 0
