@@ -55,6 +55,8 @@ constexpr int META_SC = W_BYTES;                 // up to 4 group rows of 128 fp
 constexpr int META_ZQ = W_BYTES + 1024;          // up to 4 group rows of 128 zero nibbles
 constexpr int MAX_LAYERS = 128;
 constexpr int TRACE_LAYERS = 4;
+constexpr int DS_MAX_HEADS = 256;                // (local) heads a plan may have: size of the per-head CTA-range table
+enum { ZR_QKV = 0, ZR_H = 1, ZR_GU = 2, ZR_LOGITS = 3, ZR_HALF = 4, ZR_COUNT = 5 };     // zero_share / push ranges
 constexpr unsigned long long WAIT_NS = 4000000000ull;   // any single wait longer than this aborts the launch
 
 struct alignas(64) LayerDesc
@@ -166,6 +168,15 @@ __device__ __forceinline__ uint2 lds64(uint32_t a)
     uint2 r; asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t r; asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+// 8-byte shared load that happens only when `on` (else zeros): a warp-uniform bound becomes a predicate instead of a branch
+__device__ __forceinline__ uint2 lds64_if(uint32_t a, bool on)
+{
+    uint2 r = make_uint2(0u, 0u);
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}" : "+r"(r.x), "+r"(r.y) : "r"(a), "r"((uint32_t)on));
+    return r;
+}
+// 2^x, flush-to-zero: exp(y) = ex2(y * log2 e); -inf -> 0
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d)
 {
@@ -183,6 +194,16 @@ __device__ __forceinline__ void imma_z(int (&c)[4], uint32_t a0, uint32_t a1, ui
 {
     asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
         : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+// acc += w.lo * x.lo + w.hi * x.hi for two packed fp16 pairs: mixed-precision FMA (fma.rn.f32.f16 -> SASS FHFMA, fp16 x fp16 + fp32, one
+// rounding).  The product of two fp16 values is exact in fp32, so this is bit-identical to converting both to fp32 and fmaf() -- without
+// the four conversions.
+__device__ __forceinline__ float fhfma2(uint32_t w, uint32_t x, float acc)
+{
+    asm("{\n\t.reg .b16 wl, wh, xl, xh;\n\tmov.b32 {wl, wh}, %1;\n\tmov.b32 {xl, xh}, %2;\n\t"
+        "fma.rn.f32.f16 %0, wl, xl, %0;\n\tfma.rn.f32.f16 %0, wh, xh, %0;\n\t}" : "+f"(acc) : "r"(w), "r"(x));
+    return acc;
 }
 
 __device__ __forceinline__ half silu_h(half x)
@@ -275,11 +296,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     float* q_s = parts + 2 * 17 * PART_LD;                                             // [2][128] scaled q of the segment's head
     float* kn_s = q_s + 2 * TILE;                                                      // [2][128] newest k row (after rope)
     float* vn_s = kn_s + 2 * TILE;                                                     // [2][128] newest v row
-    unsigned char* wnorm = reinterpret_cast<unsigned char*>(vn_s + 2 * TILE);          // [H / 8][16 B]: norm weights of the rows this CTA quantises next (by k8-row slot)
+    half* qh_s = reinterpret_cast<half*>(vn_s + 2 * TILE);                             // [2][128] q of the segment's head after rope, fp16 as the reference holds it (unscaled)
+    unsigned char* wnorm = reinterpret_cast<unsigned char*>(qh_s + 2 * TILE);          // [H / 8][16 B]: norm weights of the rows this CTA quantises next (by k8-row slot)
     half* xh = reinterpret_cast<half*>(xs);                                            // HEAD: normalised x [H] (xs is free by then)
     __shared__ __align__(8) unsigned long long full_bar[4 * MAX_DEPTH], empty_bar[4 * MAX_DEPTH];
     __shared__ float s_red[DS_NCW];
     __shared__ unsigned long long s_base, s_base_x;
+    // The schedule does not depend on the layer (nor, except ATT, on anything but the shapes): this CTA's unit range of every phase,
+    // its shares of the buffers it zeroes and the CTA range of every head's attention units are computed ONCE per launch.  (They were
+    // 64-bit divisions re-done by every thread in every phase of every layer: 5 % of all instructions executed, in the prologues.)
+    __shared__ int s_rng[6][4];                                  // [phase kind]{lo, hi, first K stage lo % spt, K stages to quantise min(hi - lo, spt)}
+    __shared__ int s_zr[ZR_COUNT][2];                            // [buffer][lo, hi) in units of 4 floats (ZR_HALF: 2 floats)
+    __shared__ unsigned short s_clo[DS_MAX_HEADS], s_chi[DS_MAX_HEADS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -287,6 +315,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     if (tid == 0) {
         for (int i = 0; i < nst; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid >= 32 && tid < 38) {
+        const Phase p = phase_of(a, tid - 32, G);
+        const int lo = range_lo(p.U, cta, p.G), hi = range_lo(p.U, cta + 1, p.G);
+        s_rng[tid - 32][0] = lo; s_rng[tid - 32][1] = hi;
+        s_rng[tid - 32][2] = (p.spt > 0 && hi > lo) ? lo % p.spt : 0;
+        s_rng[tid - 32][3] = p.spt > 0 ? min(hi - lo, p.spt) : 0;
+    } else if (tid >= 64 && tid < 64 + ZR_COUNT) {
+        const int k = tid - 64;
+        const int n = k == ZR_QKV ? (3 * a.HQ) >> 2 : (k == ZR_H ? a.H >> 2 : (k == ZR_GU ? (2 * a.I) >> 2 : (k == ZR_LOGITS ? a.vocab >> 2 : a.H >> 1)));
+        s_zr[k][0] = share_lo(n, cta, G); s_zr[k][1] = share_lo(n, cta + 1, G);
+    } else if (tid >= 128 && tid < 128 + a.heads) {
+        const Phase pa = phase_of(a, PH_ATT, G);
+        const int h = tid - 128;
+        s_clo[h] = (unsigned short)cta_of((long long)h * pa.tpm, pa.U, pa.G);
+        s_chi[h] = (unsigned short)cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, pa.G);
     }
     __syncthreads();
 
@@ -311,13 +355,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             #pragma unroll 1
             for (int ph = PH_QKV; ph <= PH_DOWN; ph++) {
                 const Phase p = phase_of(a, ph, G);
-                const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
+                const int u0 = s_rng[ph][0], u1 = s_rng[ph][1];
                 const int i0 = ((pq - jbase) & 3);
                 jbase += u1 - u0;
                 if (ph == PH_ATT) {
+                    int h = (u0 + i0) / p.tpm, ch = (u0 + i0) - h * p.tpm;
                     #pragma unroll 1
                     for (int u = u0 + i0; u < u1; u += 4) {
-                        const int h = u / p.tpm, ch = u - h * p.tpm;
                         const int pos0 = ch * 16;
                         int nv = a.past_len - pos0; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
                         const uint32_t base = acquire((uint32_t)nv * 512u);
@@ -327,6 +371,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                             if (lane == 1) bulk_g2s(base + 4096, L->vc + off, (uint32_t)nv * 256u, full0 + ls * 8);
                         }
                         advance();
+                        ch += 4;
+                        while (ch >= p.tpm) { ch -= p.tpm; h++; }
                     }
                     continue;
                 }
@@ -349,8 +395,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
         }
         {
-            const Phase p = phase_of(a, PH_HEAD, G);
-            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
+            const int u0 = s_rng[PH_HEAD][0], u1 = s_rng[PH_HEAD][1];
             const int i0 = ((pq - jbase) & 3);
             const long long total = (long long)a.vocab * a.H * 2;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.lm_head);
@@ -386,14 +431,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     unsigned long long target = s_base + (unsigned long long)G;
     const unsigned epoch0 = (unsigned)s_base_x * (unsigned)(2 * a.n_layers) + 1u;      // epoch of (layer l, o / down) = epoch0 + 2 l + {0, 1}
 
-    auto zero_share = [&](float* buf, int n) {            // this CTA's share of a float buffer (n % 4 == 0)
-        const int lo = share_lo(n >> 2, cta, G), hi = share_lo(n >> 2, cta + 1, G);
+    auto zero_share = [&](float* buf, int which) {        // this CTA's share of a float buffer (its length % 4 == 0)
+        const int lo = s_zr[which][0], hi = s_zr[which][1];
         for (int i = lo + tid; i < hi; i += DS_CONSUMERS) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     };
 
     // ---- launch start: all accumulators and the logits to zero (robust against an aborted previous launch), then barrier ----
-    zero_share(a.acc_qkv, 3 * a.HQ); zero_share(a.acc_o, a.H); zero_share(a.acc_gu, 2 * a.I); zero_share(a.acc_d, a.H);
-    if (a.logits) zero_share(a.logits, a.vocab);
+    zero_share(a.acc_qkv, ZR_QKV); zero_share(a.acc_o, ZR_H); zero_share(a.acc_gu, ZR_GU); zero_share(a.acc_d, ZR_H);
+    if (a.logits) zero_share(a.logits, ZR_LOGITS);
     for (int i = tid; i < a.H / 8; i += DS_CONSUMERS)
         reinterpret_cast<uint4*>(xres)[i] = __ldg(reinterpret_cast<const uint4*>(a.x_in) + i);
 
@@ -404,8 +449,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     // accumulator) instead of two.  Slot r of wnorm holds the weights of row r of the staging order.
     auto preload_norm = [&](const half* nw, const Phase& p) {
         if constexpr (ACT) return;                          // act-order: the getter gathers the weights itself
-        const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
-        const int n = min(u1 - u0, p.spt), s0 = u1 > u0 ? u0 % p.spt : 0;
+        const int n = s_rng[p.kind][3], s0 = s_rng[p.kind][2];
         for (int r = tid; r < n * 16; r += DS_CONSUMERS) {
             int s = s0 + (r >> 4); if (s >= p.spt) s -= p.spt;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(wnorm) + (uint32_t)r * 16u), "l"(nw + (size_t)(s * 16 + (r & 15)) * 8) : "memory");
@@ -475,7 +519,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     };
 
     // ---- quantise the K stages [s0, s0 + n) (cyclic mod spt) of the phase input into xs / segt; `get(k8, it)` yields 8 fp16 values ----
-    auto stage_x = [&](int s0, int n, int spt, auto get, int slot = 0) {
+    // RPGC = k8-rows per quantisation segment at compile time (16: groupsize >= 128, the common case: unrolled shuffles, shifts instead
+    // of divisions) or 0 = the run-time value rpg (groupsize 32 / 64)
+    auto stage_x = [&](auto rpg_c, int s0, int n, int spt, auto get, int slot) {
+        constexpr int RPGC = decltype(rpg_c)::value;
+        const int rp = RPGC ? RPGC : rpg;
         unsigned char* xs_w = xs; unsigned char* seg_w = segt;
         if constexpr (ACT) { xs_w += (size_t)slot * xs_slot; seg_w += (size_t)slot * seg_slot; }
         const int nrows = n * 16;
@@ -487,16 +535,30 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int rr = r & 15;
             const uint4 hv = act ? get(s * 16 + rr, it) : make_uint4(0, 0, 0, 0);
             float mx = row_absmax(hv);
-            for (int o = rpg >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if constexpr (RPGC != 0) {
+                #pragma unroll
+                for (int o = RPGC >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            } else {
+                for (int o = rp >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
             uint4 q;
             int sum = quantise_row(hv, mx > 0.f ? 32639.0f / mx : 0.f, q);
-            for (int o = rpg >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if constexpr (RPGC != 0) {
+                #pragma unroll
+                for (int o = RPGC >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            } else {
+                for (int o = rp >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            }
             if (act) {
                 *reinterpret_cast<uint4*>(xs_w + (size_t)s * 256 + rr * 16) = q;
-                if ((rr & (rpg - 1)) == 0)
-                    *reinterpret_cast<float2*>(seg_w + (size_t)s * 32 + (rr / rpg) * 8) = make_float2(__int_as_float(sum), mx * (1.0f / 32639.0f));
+                if ((rr & (rp - 1)) == 0)
+                    *reinterpret_cast<float2*>(seg_w + (size_t)s * 32 + (rr / rp) * 8) = make_float2(__int_as_float(sum), mx * (1.0f / 32639.0f));
             }
         }
+    };
+    auto stage_xd = [&](int s0, int n, int spt, auto get, int slot = 0) {
+        if (rpg == 16) stage_x(std::integral_constant<int, 16>{}, s0, n, spt, get, slot);
+        else stage_x(std::integral_constant<int, 0>{}, s0, n, spt, get, slot);
     };
     auto norm_get = [&](float rm) {
         return [=](int k8, int it) -> uint4 {
@@ -519,7 +581,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const int mi0 = u0 / per_mat, mi1 = ACT ? (u1 - 1) / per_mat : mi0;
         for (int mi = mi0; mi <= mi1; mi++) {
             const int ua = ACT ? max(u0, mi * per_mat) : u0, ub = ACT ? min(u1, (mi + 1) * per_mat) : u1;
-            stage_x(ua % p.spt, min(ub - ua, p.spt), p.spt, make_get(p.mat0 + mi), mi - mi0);
+            stage_xd(ua % p.spt, min(ub - ua, p.spt), p.spt, make_get(p.mat0 + mi), mi - mi0);
         }
     };
     // x (residual stream in shared memory) -> (x * rm) * w, gathered through an x_map when there is one (rms_norm.cu:118-131)
@@ -658,7 +720,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     auto push_partial = [&](const float* acc, uint2* const* push, unsigned epoch, int l, int ev) {
         grid_barrier(a.bar, target, (unsigned)G, tid);                     // the rank's partial is complete in L2
         stamp(l, ev);
-        const int lo = share_lo(a.H >> 1, cta, G), n2 = share_lo(a.H >> 1, cta + 1, G) - lo;      // in units of 2 floats
+        const int lo = s_zr[ZR_HALF][0], n2 = s_zr[ZR_HALF][1] - lo;                               // in units of 2 floats
         for (int i = tid; i < n2 * (a.tp_world - 1); i += DS_CONSUMERS) {
             int r = i / n2; const int j = i - r * n2;
             if (r >= a.tp_rank) r++;
@@ -702,12 +764,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // ======================================================== QKV ========================================================
         {
             const Phase p = phase_of(a, PH_QKV, G);
-            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
+            const int u0 = s_rng[PH_QKV][0], u1 = s_rng[PH_QKV][1];
             stamp(l, 0);
-            if (l > 0) zero_share(a.acc_gu, 2 * a.I);
+            if (l > 0) zero_share(a.acc_gu, ZR_GU);
             rm = residual_and_norm(l > 0 ? a.acc_d : nullptr, (TP && !a.tp_reduce && l > 0) ? a.slots_d : nullptr, epoch0 + 2u * (l - 1) + 1u);
             stamp(l, 15);
-            if constexpr (!ACT) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
+            if constexpr (!ACT) { if (u1 > u0) stage_xd(s_rng[p.kind][2], s_rng[p.kind][3], p.spt, norm_get(rm)); }
             else stage_phase(p, u0, u1, [&](int m) { return norm_get_map(L->ln1, rm, L->xmap[m]); });
             consumer_sync();
             stamp(l, 1);
@@ -721,8 +783,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // ======================================================== ATT ========================================================
         {
             const Phase p = phase_of(a, PH_ATT, G);
-            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
-            if (l > 0) zero_share(a.acc_d, a.H);
+            const int u0 = s_rng[PH_ATT][0], u1 = s_rng[PH_ATT][1];
+            if (l > 0) zero_share(a.acc_d, ZR_H);
             const int nph = p.tpm;
             const float scale = rsqrtf((float)TILE);
             const int l16 = lane & 15, sub = lane >> 4;
@@ -738,7 +800,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                 const float* aq = a.acc_qkv + (size_t)h * TILE;
                 const half qv = __float2half_rn(__ldcg(aq + d)), qo = __float2half_rn(__ldcg(aq + (d ^ 64)));
                 const half sn = d < 64 ? __hneg(sr[d]) : sr[d];
-                q_s[sg * TILE + d] = __half2float(__hfma(qv, cr[d], __hmul(qo, sn))) * scale;
+                const half qr = __hfma(qv, cr[d], __hmul(qo, sn));
+                qh_s[sg * TILE + d] = qr;
+                q_s[sg * TILE + d] = __half2float(qr) * scale;
                 if (owner) {
                     const float* ak = a.acc_qkv + a.HQ + (size_t)h * TILE;
                     const half kv = __float2half_rn(__ldcg(ak + d)), ko = __float2half_rn(__ldcg(ak + (d ^ 64)));
@@ -752,7 +816,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             consumer_sync();
             {
                 // this pipeline's stages, in order; the 4 warps of the pipeline take 4 positions of each 16-position chunk
-                float qf[8];
+                uint4 qh = make_uint4(0u, 0u, 0u, 0u);          // 8 fp16 q values of this lane's dims
                 float m = -INFINITY, lsum = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
                 int cur = -1;                                  // segment the running (m, l, o) belongs to
                 auto put_part = [&]() {
@@ -760,37 +824,41 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     *reinterpret_cast<float4*>(pw + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
                     if (lane == 0) { pw[128] = m; pw[129] = lsum; }
                 };
-                for (int u = u0 + ((wk - jbase) & 3); u < u1; u += 4) {
-                    const int h = u / nph, sg = h - h0, ch = u - h * nph;
+                int u = u0 + ((wk - jbase) & 3);
+                int h = u / nph, ch = u - h * nph;             // (head, chunk) of the unit, advanced without divisions
+                // 32-bit shared addresses from per-lane constants, as in the GEMV loop: K row of position wn * 4 + it * 2 + sub (16 lanes x
+                // 16 B), V row of position wn * 4 + q (32 lanes x 8 B)
+                const uint32_t k_lane = (uint32_t)((wn * 4 + sub) * 256 + l16 * 16);
+                const uint32_t v_lane = (uint32_t)(4096 + wn * 4 * 256 + lane * 8);
+                constexpr float LOG2E = 1.4426950408889634f;
+                for (; u < u1; u += 4) {
+                    const int sg = h - h0;
                     if (sg != cur) {
                         if (cur >= 0) put_part();
                         cur = sg; m = -INFINITY; lsum = 0.f; o[0] = o[1] = o[2] = o[3] = 0.f;
-                        #pragma unroll
-                        for (int j = 0; j < 8; j++) qf[j] = q_s[sg * TILE + l16 * 8 + j];
+                        qh = *reinterpret_cast<const uint4*>(qh_s + sg * TILE + l16 * 8);
                     }
                     int nv = a.past_len - ch * 16; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
-                    mbar_wait(full0 + ls * 8, par);
-                    const unsigned char* sb = ring + (size_t)(wk * depth + ls) * STAGE_STRIDE;
+                    // the zero token ties the (freely schedulable) asm loads below to the wait
+                    const uint32_t sb = ring_a + (uint32_t)ls * STAGE_STRIDE + mbar_wait_tok(full0 + ls * 8, par, false);
                     float sc2[2];
                     float smax = -INFINITY;
                     #pragma unroll
                     for (int it = 0; it < 2; it++) {
                         const int pp = wn * 4 + it * 2 + sub;
-                        const uint4 kv = *reinterpret_cast<const uint4*>(sb + pp * 256 + l16 * 16);
-                        const half2* hh = reinterpret_cast<const half2*>(&kv);
+                        const uint4 kv = lds128(sb + k_lane + it * 512);
                         float d = 0.f;
-                        #pragma unroll
-                        for (int q = 0; q < 4; q++) { const float2 f = __half22float2(hh[q]); d = fmaf(f.x, qf[2 * q], d); d = fmaf(f.y, qf[2 * q + 1], d); }
+                        d = fhfma2(kv.x, qh.x, d); d = fhfma2(kv.y, qh.y, d); d = fhfma2(kv.z, qh.z, d); d = fhfma2(kv.w, qh.w, d);
                         d += __shfl_xor_sync(0xffffffffu, d, 8); d += __shfl_xor_sync(0xffffffffu, d, 4);
                         d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 1);
-                        sc2[it] = pp < nv ? d : -INFINITY;
+                        sc2[it] = pp < nv ? d * scale : -INFINITY;
                         smax = fmaxf(smax, sc2[it]);
                     }
                     smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 16));
                     if (smax > -INFINITY && !(a.debug & 2)) {           // this warp has at least one valid position in the chunk
                         const float mnew = fmaxf(m, smax);
-                        const float alpha = __expf(m - mnew);
-                        sc2[0] = __expf(sc2[0] - mnew); sc2[1] = __expf(sc2[1] - mnew);
+                        const float alpha = ex2_ftz((m - mnew) * LOG2E);
+                        sc2[0] = ex2_ftz((sc2[0] - mnew) * LOG2E); sc2[1] = ex2_ftz((sc2[1] - mnew) * LOG2E);
                         float psum = sc2[0] + sc2[1];
                         psum += __shfl_xor_sync(0xffffffffu, psum, 16);
                         lsum = lsum * alpha + psum;
@@ -799,19 +867,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                         m = mnew;
                         #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const int pp = wn * 4 + q;
+                            // positions past the context end: weight 0 (their score is -inf) times a row that is not loaded (zeros)
                             const float wgt = __shfl_sync(0xffffffffu, sc2[q >> 1], (q & 1) * 16);
-                            if (pp < nv) {
-                                const uint2 vv = *reinterpret_cast<const uint2*>(sb + 4096 + pp * 256 + lane * 8);
-                                const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&vv.x));
-                                const float2 f1 = __half22float2(*reinterpret_cast<const half2*>(&vv.y));
-                                o[0] = fmaf(wgt, f0.x, o[0]); o[1] = fmaf(wgt, f0.y, o[1]); o[2] = fmaf(wgt, f1.x, o[2]); o[3] = fmaf(wgt, f1.y, o[3]);
-                            }
+                            const uint2 vv = lds64_if(sb + v_lane + q * 256, wn * 4 + q < nv);
+                            const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&vv.x));
+                            const float2 f1 = __half22float2(*reinterpret_cast<const half2*>(&vv.y));
+                            o[0] = fmaf(wgt, f0.x, o[0]); o[1] = fmaf(wgt, f0.y, o[1]); o[2] = fmaf(wgt, f1.x, o[2]); o[3] = fmaf(wgt, f1.y, o[3]);
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + ls * 8);
+                    // the arrive consumes values computed from every load of the stage: it cannot be scheduled before them
+                    if (lane == 0) mbar_arrive_dep(empty0 + ls * 8, o[0] + smax);
                     if (++ls == depth) { ls = 0; par ^= 1u; }
+                    ch += 4;
+                    while (ch >= nph) { ch -= nph; h++; }
                 }
                 if (cur >= 0) put_part();
                 // segments this warp saw no stage of: an empty partial
@@ -855,7 +924,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     Lt = fmaf(pp[w * PART_LD + 129], wgt, Lt);
                     ov = fmaf(pp[w * PART_LD + d], wgt, ov);
                 }
-                const int slot_id = cta - cta_of((long long)h * nph, p.U, p.G);
+                const int slot_id = cta - (int)s_clo[h];
                 float* dst = a.att_part + ((size_t)h * a.att_slots + slot_id) * PART_LD;
                 dst[d] = ov;
                 if (d == 0) { dst[128] = M; dst[129] = Lt; }
@@ -869,14 +938,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // ========================================================= O =========================================================
         {
             const Phase p = phase_of(a, PH_O, G);
-            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
-            zero_share(a.acc_qkv, 3 * a.HQ);
-            const Phase pa = phase_of(a, PH_ATT, G);
+            const int u0 = s_rng[PH_O][0], u1 = s_rng[PH_O][1];
+            zero_share(a.acc_qkv, ZR_QKV);
             // softmax-combine of the CTA partials of one head (model.py:402-409), 8 dims per thread, fp16 result.
             // All loads of up to 4 partials per round are issued together: one L2 round trip per round.
             auto combine8 = [&](int h, int d0) -> uint4 {
-                const int c_lo = cta_of((long long)h * pa.tpm, pa.U, pa.G), c_hi = cta_of((long long)(h + 1) * pa.tpm - 1, pa.U, pa.G);
-                const int ns = c_hi - c_lo + 1;
+                const int ns = (int)s_chi[h] - (int)s_clo[h] + 1;
                 const float* src = a.att_part + (size_t)h * a.att_slots * PART_LD;
                 float Lt = 0.f, ov[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY;
                 for (int b = 0; b < ns; b += 4) {
@@ -912,7 +979,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             };
             if constexpr (!ACT) {
                 // stage k of o_proj is head k: the CTA combines exactly the heads its K range needs
-                if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 { return combine8(k8 >> 4, (k8 & 15) * 8); });
+                if (u1 > u0) stage_xd(s_rng[PH_O][2], s_rng[PH_O][3], p.spt, [&](int k8, int) -> uint4 { return combine8(k8 >> 4, (k8 & 15) * 8); });
             } else {
                 // act-order o_proj: its input is a gather over ALL heads (x_map), so the combined attention output is first written
                 // to L2 once (head h by CTA h mod grid), one extra grid barrier, then every CTA gathers what its K range needs
@@ -945,9 +1012,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // ========================================================= GU ========================================================
         {
             const Phase p = phase_of(a, PH_GU, G);
-            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
+            const int u0 = s_rng[PH_GU][0], u1 = s_rng[PH_GU][1];
             rm = residual_and_norm(a.acc_o, (TP && !a.tp_reduce) ? a.slots_o : nullptr, epoch0 + 2u * l);
-            if constexpr (!ACT) { if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, norm_get(rm)); }
+            if constexpr (!ACT) { if (u1 > u0) stage_xd(s_rng[p.kind][2], s_rng[p.kind][3], p.spt, norm_get(rm)); }
             else stage_phase(p, u0, u1, [&](int m) { return norm_get_map(L->ln2, rm, L->xmap[m]); });
             consumer_sync();
             stamp(l, 9);
@@ -961,10 +1028,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // ======================================================== DOWN =======================================================
         {
             const Phase p = phase_of(a, PH_DOWN, G);
-            const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
-            zero_share(a.acc_o, a.H);
+            const int u0 = s_rng[PH_DOWN][0], u1 = s_rng[PH_DOWN][1];
+            zero_share(a.acc_o, ZR_H);
             if constexpr (!ACT) {
-                if (u1 > u0) stage_x(u0 % p.spt, min(u1 - u0, p.spt), p.spt, [&](int k8, int) -> uint4 {
+                if (u1 > u0) stage_xd(s_rng[PH_DOWN][2], s_rng[PH_DOWN][3], p.spt, [&](int k8, int) -> uint4 {
                     // silu(gate) * up on the fp16-rounded projections (q4_mlp.cu:27-36,46-88)
                     const float4 g0 = ldcg4(a.acc_gu + k8 * 8), g1 = ldcg4(a.acc_gu + k8 * 8 + 4);
                     const float4 u0v = ldcg4(a.acc_gu + a.I + k8 * 8), u1v = ldcg4(a.acc_gu + a.I + k8 * 8 + 4);
@@ -1007,7 +1074,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) reinterpret_cast<uint4*>(a.x_out)[i] = reinterpret_cast<const uint4*>(xres)[i];
     if (a.lm_head) {
         const Phase p = phase_of(a, PH_HEAD, G);
-        const int u0 = range_lo(p.U, cta, p.G), u1 = range_lo(p.U, cta + 1, p.G);
+        const int u0 = s_rng[PH_HEAD][0], u1 = s_rng[PH_HEAD][1];
         {
             const half2 rm2 = __float2half2_rn(rm);
             for (int i = tid; i < a.H / 8; i += DS_CONSUMERS) {
@@ -1035,12 +1102,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                 for (int hf = 0; hf < 2; hf++) {
                     const uint4 wv = *reinterpret_cast<const uint4*>(sb + (wn * 2 + cc) * 1024 + hf * 512 + lane * 16);
                     const uint4 xv = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(xh) + (size_t)kc * 1024 + hf * 512 + lane * 16);
-                    const half2* wh = reinterpret_cast<const half2*>(&wv); const half2* xq = reinterpret_cast<const half2*>(&xv);
-                    #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float2 fw = __half22float2(wh[q]), fx = __half22float2(xq[q]);
-                        part = fmaf(fw.x, fx.x, part); part = fmaf(fw.y, fx.y, part);
-                    }
+                    part = fhfma2(wv.x, xv.x, part); part = fhfma2(wv.y, xv.y, part);
+                    part = fhfma2(wv.z, xv.z, part); part = fhfma2(wv.w, xv.w, part);
                 }
                 if (++kc == cpr || cc == 1 || c0 + cc + 1 == nchunks) {
                     float tot = part;
@@ -1159,10 +1222,9 @@ extern "C" int exl_decode_plan_create(const exl_decode_desc* d, exl_decode_plan*
     int depth = ring_depth_for((size_t)dev_smem, fixed);
     if (const char* e = getenv("EXL_DS_DEPTH")) { int v = atoi(e); if (v >= 1 && v < depth) depth = v; }
     if (depth < 2) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: model too wide for the shared-memory plan (%d ring stages per pipeline)", depth));
-    if (d->num_heads > ds->num_sms) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: more heads (%d) than SMs", d->num_heads));
+    if (d->num_heads > ds->num_sms || d->num_heads > DS_MAX_HEADS) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: more heads (%d) than SMs (or than %d)", d->num_heads, DS_MAX_HEADS));
     a.depth = depth;
-    const int nst = 4 * depth;
-    p->smem = fixed - 1024 + (size_t)nst * STAGE_STRIDE;
+    p->smem = smem_dynamic_bytes(fixed, depth);
     if ((size_t)H * 2 > (size_t)a.spt_max * 256) return plan_fail(p, exl_set_err(EXL_ERR_ARG, "decode_plan: internal: head staging does not fit"));
     const void* kfn = step_kernel_for(any_act, d->tp_world > 1);
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);

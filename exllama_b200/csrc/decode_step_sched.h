@@ -84,13 +84,16 @@ static inline int spt_max_for(int H, int HQ, int I)
     int m = (H > I ? H : I) / TILE;
     return HQ / TILE > m ? HQ / TILE : m;
 }
+constexpr size_t SMEM_STATIC_ALLOWANCE = 2048;   // static __shared__ of the kernel (mbarriers, schedule tables): ptxas reports 1664 B
 // shared memory apart from the ring: alignment slack, x staging (+ a second slot of H / 128 stages with act-order), residual
-// stream, attention scratch, norm weights, static variables
+// stream, attention scratch (partials, q / new k / new v in fp32, q in fp16), norm weights, static variables
 static inline size_t smem_fixed_bytes(int H, int HQ, int I, bool act)
 {
     return 1024 + (size_t)(spt_max_for(H, HQ, I) + (act ? H / TILE : 0)) * (256 + 32) + (size_t)H * 2
-         + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + (size_t)H * 2 /* wnorm */ + 1024 /* static */;
+         + (size_t)(2 * 17 * PART_LD + 6 * TILE) * 4 + (size_t)2 * TILE * 2 /* fp16 q */ + (size_t)H * 2 /* wnorm */ + SMEM_STATIC_ALLOWANCE;
 }
+// dynamic shared memory to request for `depth` ring stages per pipeline
+static inline size_t smem_dynamic_bytes(size_t fixed, int depth) { return fixed - SMEM_STATIC_ALLOWANCE + (size_t)4 * depth * STAGE_STRIDE; }
 // ring stages per pipeline that fit (0: the model is too wide)
 static inline int ring_depth_for(size_t dev_smem, size_t fixed)
 {

@@ -73,7 +73,7 @@ extern "C" int ds_check(int H, int HQ, int I, int heads, int vocab, int grid, in
     const size_t fixed = smem_fixed_bytes(H, HQ, I, act != 0);
     const int depth = ring_depth_for((size_t)dev_smem, fixed);
     if (depth < 2) return fail("P7: only %lld ring stages per pipeline fit (fixed part %lld B of %lld B)", depth, (long long)fixed, dev_smem);
-    if (fixed - 1024 + (size_t)4 * depth * STAGE_STRIDE + 1024 > (size_t)dev_smem) return fail("P7: plan of %lld B exceeds %lld B", (long long)(fixed + (size_t)4 * depth * STAGE_STRIDE), dev_smem);
+    if (smem_dynamic_bytes(fixed, depth) + SMEM_STATIC_ALLOWANCE > (size_t)dev_smem) return fail("P7: plan of %lld B exceeds %lld B", (long long)(smem_dynamic_bytes(fixed, depth) + SMEM_STATIC_ALLOWANCE), dev_smem);
     if ((size_t)H * 2 > (size_t)spt_max_for(H, HQ, I) * 256) return fail("P7: normalised x of the head (%lld B) does not fit the staging area", (long long)H * 2);
     if (H % 512 || HQ % TILE || I % TILE || HQ != heads * TILE) return fail("shape: widths must be multiples of 128 (hidden of 512), HQ == heads * 128");
     if (heads > grid) return fail("shape: more heads (%lld) than CTAs (%lld)", heads, grid);
@@ -156,7 +156,7 @@ extern "C" int ds_plan(int H, int HQ, int I, int heads, int grid, int act, long 
 {
     const size_t fixed = smem_fixed_bytes(H, HQ, I, act != 0);
     *depth = ring_depth_for((size_t)dev_smem, fixed);
-    *smem = (long long)(fixed - 1024 + (size_t)4 * *depth * STAGE_STRIDE);
+    *smem = (long long)smem_dynamic_bytes(fixed, *depth);
     *att_slots = att_slots_for(grid, heads);
     return 0;
 }
