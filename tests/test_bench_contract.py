@@ -54,3 +54,20 @@ def test_bench_defaults():
     finally:
         sys.argv = argv
     assert a.gpus == 1 and a.warmup >= 3 and a.steps >= 8 and a.impl != "reference"
+
+
+def test_headline_matches_ab_evidence():
+    """DESIGN.md's numbers are the ones under profiles/: the committed headline line is the A/B winner's build (same ms / token within
+    1 %), every build of the A/B passed its parity tests, and the evidence index names files that exist."""
+    ab = json.load(open(os.path.join(ROOT, "profiles", "ab_variants_r2.json")))
+    by_tag = {v["tag"]: v for v in ab["variants"]}
+    assert all(v["rc"] == "rc=0" and "passed" in v["parity_tests"] for v in ab["variants"])
+    win = by_tag[ab["winner"]]
+    assert win["fused_ms"] == min(v["fused_ms"] for v in ab["variants"])
+    d = _line("bench_r2.json")
+    assert abs(d["ms_per_step"] - win["fused_ms"]) / win["fused_ms"] < 0.01
+    assert d["roofline"]["frac"] > 0.5 and d["step_parity"]["max_abs_diff_vs_per_op_path"] < 0.02 * d["step_parity"]["logit_rms"] + 0.02
+    import re
+    idx = open(os.path.join(ROOT, "profiles", "README.md")).read()
+    for name in re.findall(r"`([A-Za-z0-9_]+\.(?:json|jsonl|csv|txt))`", idx):
+        assert os.path.exists(os.path.join(ROOT, "profiles", name)), name
